@@ -1,0 +1,630 @@
+// api.cu -- the C ABI of libarchi_b200.so (see include/archi_b200.h for the contract and for the
+// reference interface each entry point replaces).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace archi {
+
+static thread_local char t_error[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+}
+
+// Makes `device` current for the scope of one entry point and restores the caller's device after
+// (the host process also runs PyTorch, which tracks the current device itself).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define ARCHI_DEVICE_GUARD(dev)                                              \
+    archi::DeviceGuard _guard(dev);                                          \
+    if (!_guard.ok) {                                                        \
+        archi::set_error("cudaSetDevice(%d) failed", (int)(dev));            \
+        return ARCHI_ECUDA;                                                  \
+    }
+
+static int alloc_store_buffers(archi_store *s, int64_t capacity, void **data, float **norm2, uint32_t **alive)
+{
+    *data = nullptr;
+    *norm2 = nullptr;
+    *alive = nullptr;
+    const size_t words = (size_t)((capacity + 31) / 32) + 1;
+    if (capacity > 0) {
+        ARCHI_CUDA(cudaMalloc(data, (size_t)capacity * s->ld * elt_size(s->dtype)));
+        ARCHI_CUDA(cudaMalloc(norm2, (size_t)capacity * sizeof(float)));
+    }
+    ARCHI_CUDA(cudaMalloc(alive, words * sizeof(uint32_t)));
+    ARCHI_CUDA(cudaMemset(*alive, 0, words * sizeof(uint32_t)));
+    return ARCHI_OK;
+}
+
+static void free_workspace(Workspace &w)
+{
+    if (w.part_key) cudaFree(w.part_key);
+    if (w.part_id) cudaFree(w.part_id);
+    if (w.q_dev) cudaFree(w.q_dev);
+    if (w.cursor_key) cudaFree(w.cursor_key);
+    if (w.cursor_id) cudaFree(w.cursor_id);
+    if (w.out_scores) cudaFree(w.out_scores);
+    if (w.out_ids) cudaFree(w.out_ids);
+    if (w.ev0) cudaEventDestroy(w.ev0);
+    if (w.ev1) cudaEventDestroy(w.ev1);
+    w = Workspace();
+}
+
+static int ensure_query_staging(archi_store *s, int nq)
+{
+    Workspace &w = s->ws;
+    if (w.q_cap < nq) {
+        if (w.q_dev) cudaFree(w.q_dev);
+        w.q_dev = nullptr;
+        int cap = nq < 64 ? 64 : nq;
+        ARCHI_CUDA(cudaMalloc(&w.q_dev, (size_t)cap * s->dim * sizeof(float)));
+        w.q_cap = cap;
+    }
+    if (!w.cursor_key) {
+        ARCHI_CUDA(cudaMalloc(&w.cursor_key, kMaxQB * sizeof(float)));
+        ARCHI_CUDA(cudaMalloc(&w.cursor_id, kMaxQB * sizeof(int)));
+    }
+    return ARCHI_OK;
+}
+
+static int ensure_out_staging(archi_store *s, int64_t elems)
+{
+    Workspace &w = s->ws;
+    if (w.out_cap < elems) {
+        if (w.out_scores) cudaFree(w.out_scores);
+        if (w.out_ids) cudaFree(w.out_ids);
+        w.out_scores = nullptr;
+        w.out_ids = nullptr;
+        ARCHI_CUDA(cudaMalloc(&w.out_scores, (size_t)elems * sizeof(float)));
+        ARCHI_CUDA(cudaMalloc(&w.out_ids, (size_t)elems * sizeof(int64_t)));
+        w.out_cap = elems;
+    }
+    return ARCHI_OK;
+}
+
+// The common body of archi_search / archi_hybrid_search.
+static int search_impl(archi_store *s, const float *queries, int queries_loc, int nq, int k,
+                       const uint32_t *filter_mask_dev, int include_deleted, int path, int hybrid,
+                       float w_sem, float w_bias, const float *bias_dev, float *out_scores,
+                       int64_t *out_ids, int out_loc, int64_t id_offset, void *stream)
+{
+    ARCHI_REQUIRE(s != nullptr, "search: null store");
+    ARCHI_REQUIRE(nq >= 0 && k >= 0, "search: nq=%d k=%d must be non-negative", nq, k);
+    ARCHI_REQUIRE(nq == 0 || queries != nullptr, "search: null queries");
+    ARCHI_REQUIRE(nq == 0 || k == 0 || (out_scores && out_ids), "search: null outputs");
+    ARCHI_REQUIRE(queries_loc == ARCHI_HOST || queries_loc == ARCHI_DEVICE, "search: bad queries_loc");
+    ARCHI_REQUIRE(out_loc == ARCHI_HOST || out_loc == ARCHI_DEVICE, "search: bad out_loc");
+    if (path == ARCHI_PATH_TENSOR) {
+        set_error("search: the tensor-core path is not supported in this build");
+        return ARCHI_EUNSUPPORTED;
+    }
+    ARCHI_REQUIRE(path == ARCHI_PATH_AUTO || path == ARCHI_PATH_STREAM, "search: bad path %d", path);
+    if (nq == 0 || k == 0) return ARCHI_OK;
+
+    std::lock_guard<std::mutex> lock(s->mu);
+    ARCHI_DEVICE_GUARD(s->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    const float *q_dev = queries;
+    {
+        const int rc = ensure_query_staging(s, nq);
+        if (rc != ARCHI_OK) return rc;
+    }
+    if (queries_loc == ARCHI_HOST) {
+        ARCHI_CUDA(cudaMemcpyAsync(s->ws.q_dev, queries, (size_t)nq * s->dim * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+        q_dev = s->ws.q_dev;
+    }
+    float *o_scores = out_scores;
+    int64_t *o_ids = out_ids;
+    if (out_loc == ARCHI_HOST) {
+        if (ensure_out_staging(s, (int64_t)nq * k) != ARCHI_OK) return ARCHI_ECUDA;
+        o_scores = s->ws.out_scores;
+        o_ids = s->ws.out_ids;
+    }
+    if (s->timing && !s->ws.ev0) {
+        ARCHI_CUDA(cudaEventCreate(&s->ws.ev0));
+        ARCHI_CUDA(cudaEventCreate(&s->ws.ev1));
+    }
+
+    ScanArgs a;
+    a.corpus = s->data;
+    a.dtype = s->dtype;
+    a.n = s->rows;
+    a.dim = s->dim;
+    a.ld = s->ld;
+    a.metric = s->metric;
+    a.norm2 = s->norm2;
+    a.alive = include_deleted ? nullptr : s->alive;
+    a.filter = filter_mask_dev;
+    a.hybrid = hybrid;
+    a.w_sem = w_sem;
+    a.w_bias = w_bias;
+    a.bias_stride = s->rows;
+
+    int passes = 0, grid = 0;
+    double kernel_ms = 0.0;
+    for (int q0 = 0; q0 < nq; q0 += kMaxQB) {
+        a.nqb = nq - q0 < kMaxQB ? nq - q0 : kMaxQB;
+        a.queries = q_dev + (size_t)q0 * s->dim;
+        a.bias = bias_dev ? bias_dev + (size_t)q0 * s->rows : nullptr;
+        for (int col0 = 0; col0 < k; col0 += kMaxListK) {
+            a.k = k - col0 < kMaxListK ? k - col0 : kMaxListK;
+            a.cursor_key = col0 > 0 ? s->ws.cursor_key : nullptr;
+            a.cursor_id = col0 > 0 ? s->ws.cursor_id : nullptr;
+            if (s->timing) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
+            int rc = launch_scan(s, a, st, &grid);
+            if (rc != ARCHI_OK) return rc;
+            if (s->timing) {
+                ARCHI_CUDA(cudaEventRecord(s->ws.ev1, st));
+                ARCHI_CUDA(cudaEventSynchronize(s->ws.ev1));
+                float ms = 0.f;
+                ARCHI_CUDA(cudaEventElapsedTime(&ms, s->ws.ev0, s->ws.ev1));
+                kernel_ms += ms;
+            }
+            const bool more = col0 + a.k < k;
+            rc = launch_scan_finalize(s, a, grid, k, col0, o_scores + (size_t)q0 * k, o_ids + (size_t)q0 * k,
+                                      id_offset, more ? s->ws.cursor_key : nullptr,
+                                      more ? s->ws.cursor_id : nullptr, st);
+            if (rc != ARCHI_OK) return rc;
+            ++passes;
+        }
+    }
+    s->stats.path = ARCHI_PATH_STREAM;
+    s->stats.passes = passes;
+    s->stats.grid = grid;
+    s->stats.unverified_queries = 0;
+    s->stats.last_kernel_ms = passes ? kernel_ms / passes : 0.0;
+
+    if (out_loc == ARCHI_HOST) {
+        ARCHI_CUDA(cudaMemcpyAsync(out_scores, o_scores, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+        ARCHI_CUDA(cudaMemcpyAsync(out_ids, o_ids, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        ARCHI_CUDA(cudaStreamSynchronize(st));
+    }
+    return ARCHI_OK;
+}
+
+}  // namespace archi
+
+using namespace archi;
+
+extern "C" {
+
+const char *archi_last_error(void) { return t_error; }
+int archi_abi_version(void) { return ARCHI_ABI_VERSION; }
+int64_t archi_kernel_launches(void) { return g_launches.load(); }
+
+int archi_store_create(int device, int dim, int metric, int storage_dtype, int64_t capacity_rows,
+                       archi_store_t **out)
+{
+    ARCHI_REQUIRE(out != nullptr, "store_create: null out");
+    *out = nullptr;
+    ARCHI_REQUIRE(dim >= 1 && dim <= 16384, "store_create: dim=%d out of range [1, 16384]", dim);
+    ARCHI_REQUIRE(metric == ARCHI_COSINE || metric == ARCHI_L2 || metric == ARCHI_IP,
+                  "store_create: distance_metric must be one of cosine, l2, inner_product");
+    ARCHI_REQUIRE(storage_dtype == ARCHI_F32 || storage_dtype == ARCHI_BF16,
+                  "store_create: storage dtype must be f32 or bf16");
+    ARCHI_REQUIRE(capacity_rows >= 0 && capacity_rows < (1ll << 31), "store_create: capacity out of range");
+    int ndev = 0;
+    ARCHI_CUDA(cudaGetDeviceCount(&ndev));
+    ARCHI_REQUIRE(device >= 0 && device < ndev, "store_create: device %d not present (%d visible)", device, ndev);
+    ARCHI_DEVICE_GUARD(device);
+    cudaDeviceProp prop;
+    ARCHI_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("store_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                  prop.minor);
+        return ARCHI_EUNSUPPORTED;
+    }
+    archi_store *s = new archi_store();
+    s->device = device;
+    s->dim = dim;
+    s->ld = round_up(dim, storage_dtype == ARCHI_BF16 ? 8 : 4);
+    s->metric = metric;
+    s->dtype = storage_dtype;
+    s->capacity = capacity_rows;
+    s->sm_count = prop.multiProcessorCount;
+    int rc = alloc_store_buffers(s, capacity_rows, &s->data, &s->norm2, &s->alive);
+    if (rc != ARCHI_OK) {
+        delete s;
+        return rc == ARCHI_ECUDA ? ARCHI_ENOMEM : rc;
+    }
+    *out = s;
+    return ARCHI_OK;
+}
+
+int archi_store_destroy(archi_store_t *s)
+{
+    if (!s) return ARCHI_OK;
+    ARCHI_DEVICE_GUARD(s->device);
+    cudaDeviceSynchronize();
+    if (s->data) cudaFree(s->data);
+    if (s->norm2) cudaFree(s->norm2);
+    if (s->alive) cudaFree(s->alive);
+    free_workspace(s->ws);
+    delete s;
+    return ARCHI_OK;
+}
+
+int archi_store_count(archi_store_t *s, int64_t *out_live_rows)
+{
+    ARCHI_REQUIRE(s && out_live_rows, "store_count: null argument");
+    std::lock_guard<std::mutex> lock(s->mu);
+    *out_live_rows = s->rows - s->deleted;
+    return ARCHI_OK;
+}
+
+int archi_store_rows(archi_store_t *s, int64_t *out_rows)
+{
+    ARCHI_REQUIRE(s && out_rows, "store_rows: null argument");
+    std::lock_guard<std::mutex> lock(s->mu);
+    *out_rows = s->rows;
+    return ARCHI_OK;
+}
+
+int archi_store_info(archi_store_t *s, int *dim, int *metric, int *storage_dtype, int *device,
+                     int64_t *capacity_rows)
+{
+    ARCHI_REQUIRE(s != nullptr, "store_info: null store");
+    if (dim) *dim = s->dim;
+    if (metric) *metric = s->metric;
+    if (storage_dtype) *storage_dtype = s->dtype;
+    if (device) *device = s->device;
+    if (capacity_rows) *capacity_rows = s->capacity;
+    return ARCHI_OK;
+}
+
+static int reserve_locked(archi_store *s, int64_t capacity_rows)
+{
+    if (capacity_rows <= s->capacity) return ARCHI_OK;
+    ARCHI_REQUIRE(capacity_rows < (1ll << 31), "store_reserve: capacity out of range");
+    ARCHI_DEVICE_GUARD(s->device);
+    ARCHI_CUDA(cudaDeviceSynchronize());
+    void *data;
+    float *norm2;
+    uint32_t *alive;
+    int rc = alloc_store_buffers(s, capacity_rows, &data, &norm2, &alive);
+    if (rc != ARCHI_OK) return rc == ARCHI_ECUDA ? ARCHI_ENOMEM : rc;
+    if (s->rows > 0) {
+        ARCHI_CUDA(cudaMemcpy(data, s->data, (size_t)s->rows * s->ld * elt_size(s->dtype), cudaMemcpyDeviceToDevice));
+        ARCHI_CUDA(cudaMemcpy(norm2, s->norm2, (size_t)s->rows * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    ARCHI_CUDA(cudaMemcpy(alive, s->alive, (size_t)((s->capacity + 31) / 32 + 1) * sizeof(uint32_t),
+                          cudaMemcpyDeviceToDevice));
+    if (s->data) cudaFree(s->data);
+    if (s->norm2) cudaFree(s->norm2);
+    cudaFree(s->alive);
+    s->data = data;
+    s->norm2 = norm2;
+    s->alive = alive;
+    s->capacity = capacity_rows;
+    return ARCHI_OK;
+}
+
+int archi_store_reserve(archi_store_t *s, int64_t capacity_rows)
+{
+    ARCHI_REQUIRE(s != nullptr, "store_reserve: null store");
+    std::lock_guard<std::mutex> lock(s->mu);
+    return reserve_locked(s, capacity_rows);
+}
+
+int archi_store_reset(archi_store_t *s)
+{
+    ARCHI_REQUIRE(s != nullptr, "store_reset: null store");
+    std::lock_guard<std::mutex> lock(s->mu);
+    ARCHI_DEVICE_GUARD(s->device);
+    ARCHI_CUDA(cudaDeviceSynchronize());
+    ARCHI_CUDA(cudaMemset(s->alive, 0, (size_t)((s->capacity + 31) / 32 + 1) * sizeof(uint32_t)));
+    s->rows = 0;
+    s->deleted = 0;
+    return ARCHI_OK;
+}
+
+int archi_store_append(archi_store_t *s, const void *rows, int src_dtype, int src_loc, int64_t n, void *stream,
+                       int64_t *out_first_row)
+{
+    ARCHI_REQUIRE(s != nullptr, "store_append: null store");
+    ARCHI_REQUIRE(n >= 0, "store_append: n < 0");
+    ARCHI_REQUIRE(n == 0 || rows != nullptr, "store_append: null rows");
+    ARCHI_REQUIRE(src_dtype == ARCHI_F32 || src_dtype == ARCHI_BF16, "store_append: source dtype must be f32 or bf16");
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (out_first_row) *out_first_row = s->rows;
+    if (n == 0) return ARCHI_OK;
+    ARCHI_DEVICE_GUARD(s->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (s->rows + n > s->capacity) {
+        int64_t want = s->capacity * 2 > s->rows + n ? s->capacity * 2 : s->rows + n;
+        if (want < 1024) want = 1024;
+        if (want >= (1ll << 31)) want = (1ll << 31) - 1;
+        if (want < s->rows + n) {
+            set_error("store_append: %lld rows exceed the per-shard limit", (long long)(s->rows + n));
+            return ARCHI_ENOMEM;
+        }
+        int rc = reserve_locked(s, want);
+        if (rc != ARCHI_OK) return rc;
+    }
+    const void *src_dev = rows;
+    void *tmp = nullptr;
+    if (src_loc == ARCHI_HOST) {
+        const size_t bytes = (size_t)n * s->dim * elt_size(src_dtype);
+        ARCHI_CUDA(cudaMallocAsync(&tmp, bytes, st));
+        ARCHI_CUDA(cudaMemcpyAsync(tmp, rows, bytes, cudaMemcpyHostToDevice, st));
+        src_dev = tmp;
+    }
+    int rc = launch_append(s, src_dev, src_dtype, s->rows, n, st);
+    if (tmp) {
+        cudaFreeAsync(tmp, st);
+        cudaStreamSynchronize(st);  // the host buffer may be reused by the caller
+    }
+    if (rc != ARCHI_OK) return rc;
+    s->rows += n;
+    return ARCHI_OK;
+}
+
+int archi_store_delete_rows(archi_store_t *s, const int64_t *rows_host, int64_t n)
+{
+    ARCHI_REQUIRE(s != nullptr, "store_delete_rows: null store");
+    ARCHI_REQUIRE(n >= 0 && (n == 0 || rows_host), "store_delete_rows: bad arguments");
+    if (n == 0) return ARCHI_OK;
+    std::lock_guard<std::mutex> lock(s->mu);
+    ARCHI_DEVICE_GUARD(s->device);
+    long long *rows_dev = nullptr;
+    int *changed_dev = nullptr;
+    ARCHI_CUDA(cudaMalloc(&rows_dev, (size_t)n * sizeof(long long)));
+    ARCHI_CUDA(cudaMalloc(&changed_dev, sizeof(int)));
+    ARCHI_CUDA(cudaMemset(changed_dev, 0, sizeof(int)));
+    ARCHI_CUDA(cudaMemcpy(rows_dev, rows_host, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
+    int rc = launch_delete_rows(s, rows_dev, n, changed_dev, 0);
+    int changed = 0;
+    if (rc == ARCHI_OK) {
+        ARCHI_CUDA(cudaMemcpy(&changed, changed_dev, sizeof(int), cudaMemcpyDeviceToHost));
+        s->deleted += changed;
+    }
+    cudaFree(rows_dev);
+    cudaFree(changed_dev);
+    return rc;
+}
+
+int archi_store_read_rows(archi_store_t *s, int64_t first_row, int64_t n, float *out_host)
+{
+    ARCHI_REQUIRE(s != nullptr && (n == 0 || out_host), "store_read_rows: null argument");
+    std::lock_guard<std::mutex> lock(s->mu);
+    ARCHI_REQUIRE(first_row >= 0 && n >= 0 && first_row + n <= s->rows, "store_read_rows: range [%lld, %lld) outside [0, %lld)",
+                  (long long)first_row, (long long)(first_row + n), (long long)s->rows);
+    if (n == 0) return ARCHI_OK;
+    ARCHI_DEVICE_GUARD(s->device);
+    float *tmp = nullptr;
+    ARCHI_CUDA(cudaMalloc(&tmp, (size_t)n * s->dim * sizeof(float)));
+    int rc = launch_read_rows(s, first_row, n, tmp, 0);
+    if (rc == ARCHI_OK)
+        ARCHI_CUDA(cudaMemcpy(out_host, tmp, (size_t)n * s->dim * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(tmp);
+    return rc;
+}
+
+// ---- snapshot / restore -------------------------------------------------------------------------
+struct SnapshotHeader {
+    char magic[8];  // "ARCHIB2\0"
+    int32_t version, dim, ld, metric, dtype, reserved;
+    int64_t rows, deleted;
+};
+
+static int copy_dev_to_file(FILE *f, const void *dev, size_t bytes)
+{
+    const size_t chunk = 64u << 20;
+    std::vector<char> buf(bytes < chunk ? bytes : chunk);
+    for (size_t off = 0; off < bytes; off += chunk) {
+        const size_t nb = bytes - off < chunk ? bytes - off : chunk;
+        ARCHI_CUDA(cudaMemcpy(buf.data(), (const char *)dev + off, nb, cudaMemcpyDeviceToHost));
+        if (fwrite(buf.data(), 1, nb, f) != nb) {
+            set_error("store_save: short write");
+            return ARCHI_EIO;
+        }
+    }
+    return ARCHI_OK;
+}
+
+static int copy_file_to_dev(FILE *f, void *dev, size_t bytes)
+{
+    const size_t chunk = 64u << 20;
+    std::vector<char> buf(bytes < chunk ? bytes : chunk);
+    for (size_t off = 0; off < bytes; off += chunk) {
+        const size_t nb = bytes - off < chunk ? bytes - off : chunk;
+        if (fread(buf.data(), 1, nb, f) != nb) {
+            set_error("store_load: short read");
+            return ARCHI_EIO;
+        }
+        ARCHI_CUDA(cudaMemcpy((char *)dev + off, buf.data(), nb, cudaMemcpyHostToDevice));
+    }
+    return ARCHI_OK;
+}
+
+int archi_store_save(archi_store_t *s, const char *path)
+{
+    ARCHI_REQUIRE(s && path, "store_save: null argument");
+    std::lock_guard<std::mutex> lock(s->mu);
+    ARCHI_DEVICE_GUARD(s->device);
+    ARCHI_CUDA(cudaDeviceSynchronize());
+    FILE *f = fopen(path, "wb");
+    if (!f) {
+        set_error("store_save: cannot open %s", path);
+        return ARCHI_EIO;
+    }
+    SnapshotHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "ARCHIB2", 8);
+    h.version = 1;
+    h.dim = s->dim;
+    h.ld = s->ld;
+    h.metric = s->metric;
+    h.dtype = s->dtype;
+    h.rows = s->rows;
+    h.deleted = s->deleted;
+    int rc = fwrite(&h, sizeof(h), 1, f) == 1 ? ARCHI_OK : ARCHI_EIO;
+    if (rc == ARCHI_OK && s->rows > 0) {
+        rc = copy_dev_to_file(f, s->data, (size_t)s->rows * s->ld * elt_size(s->dtype));
+        if (rc == ARCHI_OK) rc = copy_dev_to_file(f, s->norm2, (size_t)s->rows * sizeof(float));
+        if (rc == ARCHI_OK) rc = copy_dev_to_file(f, s->alive, (size_t)((s->rows + 31) / 32) * sizeof(uint32_t));
+    }
+    fclose(f);
+    if (rc == ARCHI_EIO && t_error[0] == 0) set_error("store_save: write failed");
+    return rc;
+}
+
+int archi_store_load(const char *path, int device, archi_store_t **out)
+{
+    ARCHI_REQUIRE(path && out, "store_load: null argument");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        set_error("store_load: cannot open %s", path);
+        return ARCHI_EIO;
+    }
+    SnapshotHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "ARCHIB2", 8) != 0 || h.version != 1) {
+        fclose(f);
+        set_error("store_load: %s is not an archi_b200 snapshot", path);
+        return ARCHI_EIO;
+    }
+    archi_store *s = nullptr;
+    int rc = archi_store_create(device, h.dim, h.metric, h.dtype, h.rows, &s);
+    if (rc != ARCHI_OK) {
+        fclose(f);
+        return rc;
+    }
+    if (h.rows > 0) {
+        rc = copy_file_to_dev(f, s->data, (size_t)h.rows * s->ld * elt_size(s->dtype));
+        if (rc == ARCHI_OK) rc = copy_file_to_dev(f, s->norm2, (size_t)h.rows * sizeof(float));
+        if (rc == ARCHI_OK) rc = copy_file_to_dev(f, s->alive, (size_t)((h.rows + 31) / 32) * sizeof(uint32_t));
+    }
+    fclose(f);
+    if (rc != ARCHI_OK) {
+        archi_store_destroy(s);
+        return rc;
+    }
+    s->rows = h.rows;
+    s->deleted = h.deleted;
+    *out = s;
+    return ARCHI_OK;
+}
+
+// ---- pool + normalise -----------------------------------------------------------------------------
+int archi_pool_normalize(const void *hidden_dev, int hidden_dtype, const void *mask_dev, int mask_dtype, int B, int L,
+                         int H, void *out_bf16_dev, float *out_f32_dev, void *stream)
+{
+    ARCHI_REQUIRE(B == 0 || (hidden_dev && mask_dev), "pool_normalize: null input");
+    return launch_pool_normalize(hidden_dev, hidden_dtype, mask_dev, mask_dtype, B, L, H, nullptr, ARCHI_F32, 0,
+                                 nullptr, nullptr, 0, out_bf16_dev, out_f32_dev,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+int archi_pool_normalize_append(archi_store_t *s, const void *hidden_dev, int hidden_dtype, const void *mask_dev,
+                                int mask_dtype, int B, int L, float *out_f32_dev, void *stream,
+                                int64_t *out_first_row)
+{
+    ARCHI_REQUIRE(s != nullptr, "pool_normalize_append: null store");
+    ARCHI_REQUIRE(B >= 0 && (B == 0 || (hidden_dev && mask_dev)), "pool_normalize_append: bad input");
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (out_first_row) *out_first_row = s->rows;
+    if (B == 0) return ARCHI_OK;
+    ARCHI_DEVICE_GUARD(s->device);
+    if (s->rows + B > s->capacity) {
+        int64_t want = s->capacity * 2 > s->rows + B ? s->capacity * 2 : s->rows + B;
+        if (want < 1024) want = 1024;
+        int rc = reserve_locked(s, want);
+        if (rc != ARCHI_OK) return rc;
+    }
+    char *rows = (char *)s->data + (size_t)s->rows * s->ld * elt_size(s->dtype);
+    int rc = launch_pool_normalize(hidden_dev, hidden_dtype, mask_dev, mask_dtype, B, L, s->dim, rows, s->dtype,
+                                   s->ld, s->norm2 + s->rows, s->alive, s->rows, nullptr, out_f32_dev,
+                                   reinterpret_cast<cudaStream_t>(stream));
+    if (rc != ARCHI_OK) return rc;
+    s->rows += B;
+    return ARCHI_OK;
+}
+
+// ---- search -------------------------------------------------------------------------------------------
+int archi_search(archi_store_t *s, const float *queries, int queries_loc, int nq, int k,
+                 const uint32_t *filter_mask_dev, int include_deleted, int path, float *out_scores,
+                 int64_t *out_ids, int out_loc, int64_t id_offset, void *stream)
+{
+    return search_impl(s, queries, queries_loc, nq, k, filter_mask_dev, include_deleted, path, 0, 1.f, 0.f, nullptr,
+                       out_scores, out_ids, out_loc, id_offset, stream);
+}
+
+int archi_hybrid_search(archi_store_t *s, const float *queries, int queries_loc, int nq, int k, float w_sem,
+                        float w_bm25, const float *bm25_dev, const uint32_t *filter_mask_dev, int include_deleted,
+                        float *out_scores, int64_t *out_ids, int out_loc, int64_t id_offset, void *stream)
+{
+    return search_impl(s, queries, queries_loc, nq, k, filter_mask_dev, include_deleted, ARCHI_PATH_STREAM, 1, w_sem,
+                       w_bm25, bm25_dev, out_scores, out_ids, out_loc, id_offset, stream);
+}
+
+int archi_bm25_accumulate(const int64_t *post_ptr_host, int n_terms, const float *idf_host,
+                          const int32_t *doc_ids_dev, const int32_t *tfs_dev, const float *doc_len_dev,
+                          float avgdl, float k1, float b, float sign, float *out_dev, void *stream)
+{
+    ARCHI_REQUIRE(n_terms >= 0, "bm25_accumulate: n_terms < 0");
+    ARCHI_REQUIRE(n_terms == 0 || (post_ptr_host && idf_host && out_dev && doc_len_dev),
+                  "bm25_accumulate: null argument");
+    ARCHI_REQUIRE(avgdl > 0.f, "bm25_accumulate: avgdl must be positive");
+    for (int t = 0; t < n_terms; ++t) {
+        const int64_t b0 = post_ptr_host[t], b1 = post_ptr_host[t + 1];
+        ARCHI_REQUIRE(b1 >= b0, "bm25_accumulate: posting pointers must be non-decreasing");
+        int rc = launch_bm25(doc_ids_dev + b0, tfs_dev + b0, b1 - b0, idf_host[t], doc_len_dev, avgdl, k1, b, sign,
+                             out_dev, reinterpret_cast<cudaStream_t>(stream));
+        if (rc != ARCHI_OK) return rc;
+    }
+    return ARCHI_OK;
+}
+
+int archi_merge_topk(int device, const float *scores_dev, const int64_t *ids_dev, int n_lists, int nq, int k,
+                     int larger_is_better, float *out_scores_dev, int64_t *out_ids_dev, void *stream)
+{
+    ARCHI_REQUIRE(nq >= 0 && k >= 0, "merge_topk: negative size");
+    ARCHI_REQUIRE(nq == 0 || k == 0 || (scores_dev && ids_dev && out_scores_dev && out_ids_dev),
+                  "merge_topk: null argument");
+    ARCHI_DEVICE_GUARD(device);
+    return launch_merge_lists(scores_dev, ids_dev, n_lists, nq, k, larger_is_better, out_scores_dev, out_ids_dev,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int archi_store_last_stats(archi_store_t *s, archi_search_stats_t *out)
+{
+    ARCHI_REQUIRE(s && out, "store_last_stats: null argument");
+    std::lock_guard<std::mutex> lock(s->mu);
+    *out = s->stats;
+    return ARCHI_OK;
+}
+
+int archi_store_set_timing(archi_store_t *s, int enabled)
+{
+    ARCHI_REQUIRE(s != nullptr, "store_set_timing: null store");
+    std::lock_guard<std::mutex> lock(s->mu);
+    s->timing = enabled != 0;
+    return ARCHI_OK;
+}
+
+}  // extern "C"

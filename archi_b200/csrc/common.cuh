@@ -1,0 +1,140 @@
+// common.cuh -- shared declarations for libarchi_b200.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "../../include/archi_b200.h"
+
+namespace archi {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define ARCHI_CUDA(call)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            archi::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                \
+                             cudaGetErrorString(_e));                                            \
+            return ARCHI_ECUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+#define ARCHI_CHECK_LAUNCH()                                                                     \
+    do {                                                                                         \
+        archi::g_launches.fetch_add(1, std::memory_order_relaxed);                               \
+        ARCHI_CUDA(cudaGetLastError());                                                          \
+    } while (0)
+
+#define ARCHI_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                         \
+        if (!(cond)) {                                                                           \
+            archi::set_error(__VA_ARGS__);                                                       \
+            return ARCHI_EINVAL;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// the store (one row shard resident in one GPU's HBM)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxListK = 128;     // entries a warp-register list holds (4 per lane)
+constexpr int kScanThreads = 256;  // 8 warps per CTA
+constexpr int kMaxQB = 8;          // queries per corpus pass on the streaming path
+
+struct Workspace {
+    // per-CTA partial lists of the streaming scan: [grid][kMaxQB][kMaxListK]
+    float *part_key = nullptr;
+    int *part_id = nullptr;
+    int part_grid = 0;
+    // per-pass query staging and multi-pass cursors
+    float *q_dev = nullptr;        // [q_cap, dim]
+    int q_cap = 0;
+    float *cursor_key = nullptr;   // [q_cap]
+    int *cursor_id = nullptr;      // [q_cap]
+    float *out_scores = nullptr;   // [q_cap * k_cap] device staging for host outputs
+    int64_t *out_ids = nullptr;
+    int64_t out_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+}  // namespace archi
+
+struct archi_store {
+    int device = 0;
+    int dim = 0;
+    int ld = 0;               // row stride in elements (dim rounded up to a 16-byte multiple)
+    int metric = 0;
+    int dtype = 0;            // ARCHI_F32 | ARCHI_BF16
+    int64_t capacity = 0;
+    int64_t rows = 0;         // appended so far (next row id)
+    int64_t deleted = 0;
+    void *data = nullptr;     // [capacity, ld] storage dtype
+    float *norm2 = nullptr;   // [capacity] |row|^2 of the stored values
+    uint32_t *alive = nullptr;// [capacity/32] tombstone bitmask (1 = live)
+    int sm_count = 0;
+    int timing = 0;
+    archi_search_stats_t stats{};
+    archi::Workspace ws;
+    std::mutex mu;
+};
+
+namespace archi {
+
+inline size_t elt_size(int dtype) { return dtype == ARCHI_BF16 ? 2 : 4; }
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------
+// launchers implemented in the .cu files (all enqueue on `st`, no host sync)
+// ---------------------------------------------------------------------------------------------
+struct ScanArgs {
+    const void *corpus;
+    int dtype;
+    int64_t n;
+    int dim, ld;
+    int metric;
+    const float *queries;     // device [nqb, dim]
+    int nqb;                  // 1..kMaxQB
+    int k;                    // 1..kMaxListK (entries to produce this pass)
+    const float *norm2;       // [n]
+    const uint32_t *alive;    // may be null
+    const uint32_t *filter;   // may be null
+    int hybrid;
+    const float *bias;        // [nqb][bias_stride] or null
+    int64_t bias_stride;
+    float w_sem, w_bias;
+    const float *cursor_key;  // [nqb] or null: only rows sorting strictly after the cursor
+    const int *cursor_id;
+};
+
+// Streaming scan: fills ws.part_* with per-CTA lists; returns grid in *grid_out.
+int launch_scan(archi_store *s, const ScanArgs &a, cudaStream_t st, int *grid_out);
+// Merges `grid` per-CTA lists into the final rows [col0, col0+k) of the outputs, converts keys to
+// the reference's score convention and (optionally) records the cursor for the next pass.
+int launch_scan_finalize(archi_store *s, const ScanArgs &a, int grid, int k_total, int col0,
+                         float *out_scores, int64_t *out_ids, int64_t id_offset,
+                         float *cursor_key_out, int *cursor_id_out, cudaStream_t st);
+
+int launch_append(archi_store *s, const void *src_dev, int src_dtype, int64_t first_row, int64_t n,
+                  cudaStream_t st);
+int launch_delete_rows(archi_store *s, const long long *rows_dev, int64_t n, int *changed_dev,
+                       cudaStream_t st);
+int launch_read_rows(archi_store *s, int64_t first_row, int64_t n, float *out_dev, cudaStream_t st);
+int launch_pool_normalize(const void *hidden, int hidden_dtype, const void *mask, int mask_dtype,
+                          int B, int L, int H, void *store_rows, int store_dtype, int store_ld,
+                          float *store_norm2, uint32_t *alive, long long first_row, void *out_bf16,
+                          float *out_f32, cudaStream_t st);
+int launch_bm25(const int32_t *doc_ids, const int32_t *tfs, int64_t n_post, float idf,
+                const float *doc_len, float avgdl, float k1, float b, float sign, float *out,
+                cudaStream_t st);
+int launch_merge_lists(const float *scores, const int64_t *ids, int n_lists, int nq, int k,
+                       int larger_is_better, float *out_scores, int64_t *out_ids, cudaStream_t st);
+
+}  // namespace archi

@@ -1,0 +1,119 @@
+// topk.cuh -- warp-level register top-k (shuffle/ballot) and the warp multi-value reduction.
+//
+// A WarpTopK<M> is a sorted list of 32*M (key, id) entries distributed over the 32 lanes of a
+// warp: rank r lives in slot r/32 of lane r%32.  Larger key = better; equal keys are ordered by
+// the lower id, which is the tie rule the oracle uses.  All member functions are warp-collective
+// and must be called with warp-uniform arguments.
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math_constants.h>
+
+namespace archi {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ bool better(float ak, int ai, float bk, int bi)
+{
+    return ak > bk || (ak == bk && ai < bi);
+}
+
+template <int M>
+struct WarpTopK {
+    float key[M];
+    int id[M];
+
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int s = 0; s < M; ++s) {
+            key[s] = -CUDART_INF_F;
+            id[s] = INT_MAX;
+        }
+    }
+
+    // Insert (nk, nid) keeping the best k entries in ranks [0, k).  Returns true when the list
+    // changed.  NaN keys must be filtered by the caller.
+    __device__ __forceinline__ bool insert(float nk, int nid, int k, int lane)
+    {
+        int p = 0;
+#pragma unroll
+        for (int s = 0; s < M; ++s)
+            p += __popc(__ballot_sync(kFull, better(key[s], id[s], nk, nid)));
+        if (p >= k) return false;
+#pragma unroll
+        for (int s = M - 1; s >= 0; --s) {
+            float pk = __shfl_up_sync(kFull, key[s], 1);
+            int pi = __shfl_up_sync(kFull, id[s], 1);
+            if (s > 0) {
+                float ck = __shfl_sync(kFull, key[s - 1], 31);
+                int ci = __shfl_sync(kFull, id[s - 1], 31);
+                if (lane == 0) {
+                    pk = ck;
+                    pi = ci;
+                }
+            }
+            const int rank = s * 32 + lane;
+            if (rank == p) {
+                key[s] = nk;
+                id[s] = nid;
+            } else if (rank > p) {
+                key[s] = pk;
+                id[s] = pi;
+            }
+        }
+        return true;
+    }
+
+    // The entry at rank k-1 (the admission threshold), broadcast to all lanes.
+    __device__ __forceinline__ void threshold(int k, float &tk, int &ti) const
+    {
+        const int ss = (k - 1) >> 5, ll = (k - 1) & 31;
+        float a = key[0];
+        int b = id[0];
+#pragma unroll
+        for (int s = 1; s < M; ++s)
+            if (ss == s) {
+                a = key[s];
+                b = id[s];
+            }
+        tk = __shfl_sync(kFull, a, ll);
+        ti = __shfl_sync(kFull, b, ll);
+    }
+};
+
+// Sum NV per-lane values across the warp with NV-1+log2(32/NV) shuffles (instead of 5*NV): at each
+// stage half of the values move to the partner lane.  Lane l returns the total of value
+// l >> (5 - log2(NV)).  v[] is clobbered.
+template <int NV>
+__device__ __forceinline__ float warp_multi_reduce(float (&v)[NV], int lane)
+{
+    static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8 || NV == 16 || NV == 32, "NV");
+    int d = 16;
+#pragma unroll
+    for (int cnt = NV; cnt > 1; cnt >>= 1) {
+        const bool upper = (lane & d) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt / 2; ++i) {
+            const float send = upper ? v[i] : v[i + cnt / 2];
+            const float keep = upper ? v[i + cnt / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, d);
+        }
+        d >>= 1;
+    }
+    float x = v[0];
+#pragma unroll
+    for (; d >= 1; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
+    return x;
+}
+
+template <int NV>
+struct Log2 {
+    static constexpr int value = 1 + Log2<NV / 2>::value;
+};
+template <>
+struct Log2<1> {
+    static constexpr int value = 0;
+};
+
+}  // namespace archi
