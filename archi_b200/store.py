@@ -158,12 +158,13 @@ class NativeStore:
     # ---- search --------------------------------------------------------------------------------------
     def search(self, queries, k: int, filter_mask=None, include_deleted: bool = False, id_offset: int = 0,
                path: int = N.PATH_AUTO, bm25=None, semantic_weight: float = 1.0, bm25_weight: float = 0.0,
-               hybrid: bool = False):
+               hybrid: bool = False, out=None):
         """Exact top-k.  numpy queries -> numpy (scores [nq,k] fp32, ids [nq,k] int64) through host
         buffers; torch CUDA queries -> torch CUDA outputs, nothing synchronised.
         ``filter_mask``: torch CUDA int32/uint32 bitmask words (bit i&31 of word i>>5 = row passes).
         ``hybrid``: scores are the combined score of hybrid_search; ``bm25`` is a torch CUDA fp32
-        [nq, rows] tensor (or None)."""
+        [nq, rows] tensor (or None).  ``out``: optional preallocated (scores, ids) host arrays
+        (e.g. views of pinned memory) for the numpy path."""
         k = int(k)
         fm = ctypes.c_void_p(filter_mask.data_ptr()) if filter_mask is not None else None
         bm = ctypes.c_void_p(bm25.data_ptr()) if bm25 is not None else None
@@ -180,8 +181,14 @@ class NativeStore:
         else:
             q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries, dtype=np.float32)))
             nq = q.shape[0]
-            scores = np.empty((nq, k), dtype=np.float32)
-            ids = np.empty((nq, k), dtype=np.int64)
+            if out is not None:
+                scores, ids = out
+                if scores.shape != (nq, k) or ids.shape != (nq, k) or scores.dtype != np.float32 \
+                        or ids.dtype != np.int64 or not (scores.flags.c_contiguous and ids.flags.c_contiguous):
+                    raise ValueError("out must be C-contiguous (float32 [nq,k], int64 [nq,k])")
+            else:
+                scores = np.empty((nq, k), dtype=np.float32)
+                ids = np.empty((nq, k), dtype=np.int64)
             qp, sp, ip_, loc = q.ctypes.data, scores.ctypes.data, ids.ctypes.data, N.HOST
             stream = ctypes.c_void_p(_current_stream_ptr(self.device)) if (fm or bm) else None
         if q.shape[1] != self.dim:

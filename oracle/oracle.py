@@ -255,21 +255,39 @@ def character_text_split(text: str, chunk_size: int = 1000, chunk_overlap: int =
 # --------------------------------------------------------------------------------------------
 # oracle.c via ctypes
 # --------------------------------------------------------------------------------------------
-_LIB = None
+_LIBS = {}
+
+# pgvector's own build flags [external]: its Makefile compiles the distance loops with
+# -march=native -ftree-vectorize -fassociative-math -fno-signed-zeros -fno-trapping-math, i.e. the
+# float accumulators are SIMD-reassociated.  The strict build (fast=False) keeps index order and is
+# the checker; the fast build is only the TIMED cpu baseline.
+FAST_FLAGS = ["-O3", "-march=native", "-ftree-vectorize", "-fassociative-math", "-fno-signed-zeros",
+              "-fno-trapping-math"]
 
 
-def build_clib(force: bool = False) -> str:
-    so = os.path.join(_HERE, "liboracle.so")
+def _cpu_tag() -> str:
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        key = "".join(l for l in txt.splitlines() if l.startswith(("model name", "flags")))[:20000]
+    except Exception:
+        key = "unknown"
+    return hashlib.sha1(key.encode()).hexdigest()[:10]
+
+
+def build_clib(force: bool = False, fast: bool = False) -> str:
+    # the -march=native build is tagged with the host CPU so a copy built elsewhere is never loaded
+    so = os.path.join(_HERE, f"liboracle_fast_{_cpu_tag()}.so" if fast else "liboracle.so")
     src = os.path.join(_HERE, "oracle.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-pthread", "-o", so, src, "-lm"])
+        flags = FAST_FLAGS if fast else ["-O2"]
+        subprocess.check_call(["gcc"] + flags + ["-fPIC", "-shared", "-pthread", "-o", so, src, "-lm"])
     return so
 
 
-def clib() -> ctypes.CDLL:
-    global _LIB
-    if _LIB is None:
-        lib = ctypes.CDLL(build_clib())
+def clib(fast: bool = False) -> ctypes.CDLL:
+    if fast not in _LIBS:
+        lib = ctypes.CDLL(build_clib(fast=fast))
         c_i, c_i64, c_d, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
         lib.orc_distance_f32.restype = c_d
         lib.orc_distance_f32.argtypes = [c_i, c_i, c_p, c_p]
@@ -283,8 +301,8 @@ def clib() -> ctypes.CDLL:
         lib.orc_score_from_distance.argtypes = [c_i, c_d]
         lib.orc_pool_normalize.restype = None
         lib.orc_pool_normalize.argtypes = [c_p, c_p, c_i, c_i, c_i, c_p]
-        _LIB = lib
-    return _LIB
+        _LIBS[fast] = lib
+    return _LIBS[fast]
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -303,9 +321,11 @@ def pack_mask(mask_bool: Optional[np.ndarray]) -> Optional[np.ndarray]:
 
 
 def c_scan_topk(metric: str, corpus: np.ndarray, queries: np.ndarray, k: int,
-                mask: Optional[np.ndarray] = None, nthreads: int = 1, corpus_is_bf16: bool = False):
-    """oracle.c seq scan: float accumulators, heap top-k.  corpus fp32 [N,D] or uint16 bf16 bits."""
-    lib = clib()
+                mask: Optional[np.ndarray] = None, nthreads: int = 1, corpus_is_bf16: bool = False,
+                fast: bool = False):
+    """oracle.c seq scan: float accumulators, heap top-k.  corpus fp32 [N,D] or uint16 bf16 bits.
+    ``fast`` = pgvector's own SIMD-reassociating build flags (timing only)."""
+    lib = clib(fast)
     corpus = np.ascontiguousarray(corpus, dtype=np.uint16 if corpus_is_bf16 else np.float32)
     q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
     n, d = corpus.shape

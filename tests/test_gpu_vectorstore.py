@@ -1,0 +1,262 @@
+"""GPU tests of the pool+normalise kernel and of the reference-facing surface (B200VectorStore,
+retrievers, embeddings) -- the behavioural counterparts of the reference's mocked unit tests
+(tests/unit/test_postgres_vectorstore.py), checked against the oracle instead of a mocked cursor."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- pool + normalise ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(6, 24, 64), (3, 256, 384), (33, 17, 768), (2, 5, 1024), (4, 9, 8)])
+@pytest.mark.parametrize("mask_dtype", ["i64", "i32"])
+def test_pool_normalize_matches_oracle(dtype, shape, mask_dtype):
+    import torch
+    from archi_b200.store import pool_normalize
+    B, L, H = shape
+    rng = np.random.default_rng(B * 1000 + L)
+    hidden = rng.standard_normal(shape).astype(np.float32)
+    lens = rng.integers(1, L + 1, size=B)
+    lens[0] = L
+    mask = (np.arange(L)[None, :] < lens[:, None]).astype(np.int64)
+    if B > 2:
+        mask[2, ::2] = 0                           # holes inside the sequence, not just padding
+        mask[2, 1] = 1
+    h_t = torch.from_numpy(hidden).cuda()
+    if dtype == "bf16":
+        h_t = h_t.to(torch.bfloat16)
+        hidden = h_t.float().cpu().numpy()          # the oracle sees the same (rounded) inputs
+    m_t = torch.from_numpy(mask).cuda().to(torch.int64 if mask_dtype == "i64" else torch.int32)
+    out_f32, out_bf16 = pool_normalize(h_t, m_t, want_bf16=True)
+    want = orc.pool_normalize(hidden, mask)
+    got = out_f32.cpu().numpy()
+    assert np.allclose(got, want, rtol=1e-5, atol=2e-6)
+    assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    # the bf16 copy is the round-to-nearest-even cast of the fp32 result
+    want_bits = orc.f32_to_bf16_bits(got)
+    got_bits = out_bf16.view(torch.int16).cpu().numpy().view(np.uint16)
+    assert np.array_equal(got_bits, want_bits)
+
+
+def test_pool_normalize_golden_and_all_zero_mask(golden_dir):
+    import torch
+    from archi_b200.store import pool_normalize
+    p = np.load(os.path.join(golden_dir, "pool_6x24x64.npz"))
+    out, _ = pool_normalize(torch.from_numpy(p["hidden"]).cuda(), torch.from_numpy(p["mask"]).cuda())
+    got = out.cpu().numpy()
+    assert np.allclose(got, p["pooled"], rtol=1e-5, atol=2e-6)
+    assert np.array_equal(got[4], np.zeros(64, dtype=np.float32))      # mask all zero -> zero row, no NaN
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_pool_normalize_append_equals_pool_then_append(storage):
+    import torch
+    from archi_b200.store import NativeStore, pool_normalize
+    rng = np.random.default_rng(4)
+    hidden = torch.from_numpy(rng.standard_normal((10, 12, 96)).astype(np.float32)).cuda()
+    mask = torch.ones((10, 12), dtype=torch.int64, device="cuda")
+    mask[3, 5:] = 0
+    a = NativeStore(96, "cosine", storage)
+    a.append(torch.zeros((3, 96), device="cuda"))                     # rows already present
+    assert a.pool_normalize_append(hidden, mask) == 3
+    pooled, _ = pool_normalize(hidden, mask)
+    b = NativeStore(96, "cosine", storage)
+    b.append(torch.zeros((3, 96), device="cuda"))
+    b.append(pooled)
+    assert a.rows() == b.rows() == 13 and a.count() == 13
+    assert np.array_equal(a.read_rows(0, 13), b.read_rows(0, 13))
+    q = rng.standard_normal((2, 96)).astype(np.float32)
+    ra, rb = a.search(q, 5), b.search(q, 5)
+    assert np.array_equal(ra[1], rb[1]) and np.allclose(ra[0], rb[0], rtol=1e-6, atol=1e-7)
+    a.close()
+    b.close()
+
+
+# ---- the vectorstore surface --------------------------------------------------------------------------------
+class TableEmbeddings:
+    """Deterministic stand-in for the embedding model: text -> fixed random vector (the reference's
+    tests use a MagicMock returning [0.1,0.2,0.3]*128, :44-50)."""
+
+    def __init__(self, dim=384):
+        self.dim, self.calls = dim, {"docs": 0, "query": 0}
+
+    def _vec(self, text):
+        import zlib
+        rng = np.random.default_rng(zlib.crc32(text.encode()))
+        v = rng.standard_normal(self.dim)
+        return (v / np.linalg.norm(v)).astype(np.float32)
+
+    def embed_documents(self, texts):
+        self.calls["docs"] += 1
+        return [self._vec(t).tolist() for t in texts]
+
+    def embed_query(self, text):
+        self.calls["query"] += 1
+        return self._vec(text).tolist()
+
+
+@pytest.fixture
+def fresh_store():
+    from archi_b200 import B200VectorStore
+    names = []
+
+    def make(name, **kw):
+        B200VectorStore.drop_collection(name)
+        names.append(name)
+        return B200VectorStore(pg_config={}, embedding_function=kw.pop("emb", TableEmbeddings()),
+                               collection_name=name, **kw)
+    yield make
+    for n in names:
+        B200VectorStore.drop_collection(n)
+
+
+def test_add_and_search_conventions(fresh_store):
+    from archi_b200 import Document
+    emb = TableEmbeddings()
+    vs = fresh_store("t_conv", emb=emb)
+    texts = [f"chunk number {i}" for i in range(50)]
+    metas = [{"filename": f"f{i % 5}.md", "idx": i} for i in range(50)]
+    ids = vs.add_texts(texts, metadatas=metas)
+    assert len(ids) == 50 and len(set(ids)) == 50 and emb.calls["docs"] == 1     # one embed_documents call
+    assert vs.count() == 50
+    res = vs.similarity_search_with_score("chunk number 17", k=5)
+    assert emb.calls["query"] == 1
+    assert len(res) == 5
+    doc, score = res[0]
+    assert isinstance(doc, Document) and doc.page_content == "chunk number 17"
+    assert score == pytest.approx(1.0, abs=1e-5)                                   # score = 1 - distance
+    assert doc.metadata["collection"] == "t_conv" and doc.metadata["chunk_id"] == ids[17]
+    assert doc.metadata["filename"] == "f2.md"
+    assert [s for _, s in res] == sorted((s for _, s in res), reverse=True)
+    # oracle on the same embeddings
+    corpus = np.asarray(emb.embed_documents(texts), dtype=np.float32)
+    q = np.asarray(emb.embed_query("chunk number 17"), dtype=np.float32)
+    d, i = orc.exact_topk("cosine", corpus, q, 5)
+    assert [r[0].metadata["idx"] for r in res] == i[0].tolist()
+    assert np.allclose([r[1] for r in res], 1.0 - d[0], rtol=1e-5, atol=1e-6)
+    assert [d.page_content for d in vs.similarity_search("chunk number 17", k=5)] == [r[0].page_content for r in res]
+    assert vs.similarity_search_by_vector(q.tolist(), k=2)[0].page_content == "chunk number 17"
+    # edge cases of :517-558 -- empty query, huge k, odd strings: a list comes back
+    assert len(vs.similarity_search("", k=3)) == 3
+    assert len(vs.similarity_search("chunk", k=10000)) == 50
+    assert isinstance(vs.similarity_search("'; DROP TABLE document_chunks; --", k=2), list)
+    assert isinstance(vs.similarity_search("日本語のクエリ 🚀", k=2), list)
+
+
+@pytest.mark.parametrize("metric", ["l2", "inner_product"])
+def test_distance_metrics_return_raw_distance(fresh_store, metric):
+    emb = TableEmbeddings(64)
+    vs = fresh_store(f"t_{metric}", emb=emb, distance_metric=metric)
+    texts = [f"t{i}" for i in range(40)]
+    vs.add_texts(texts)
+    res = vs.similarity_search_with_score("t3", k=4)
+    corpus = np.asarray(emb.embed_documents(texts), dtype=np.float32)
+    d, i = orc.exact_topk(metric, corpus, np.asarray(emb.embed_query("t3"), dtype=np.float32), 4)
+    assert [r[0].page_content for r in res] == [texts[j] for j in i[0]]
+    assert np.allclose([r[1] for r in res], d[0], rtol=1e-5, atol=2e-6)            # ascending distance
+    if metric == "inner_product":
+        assert res[0][1] == pytest.approx(-1.0, abs=1e-5)                           # NEGATIVE inner product
+
+
+def test_filter_delete_upsert_and_document_metadata(fresh_store):
+    vs = fresh_store("t_filter")
+    vs.register_document(7, resource_hash="abc123", display_name="Seven", source_type="web", url="http://x/7")
+    vs.register_document(8, resource_hash="def456")
+    vs.add_texts([f"seven {i}" for i in range(6)], metadatas=[{"kind": "a", "n": i} for i in range(6)], document_id=7)
+    ids8 = vs.add_texts([f"eight {i}" for i in range(4)], metadatas=[{"kind": "b"} for _ in range(4)], document_id=8)
+    vs.add_texts(["loose chunk"], metadatas=[None and {} or {}])
+    assert vs.count() == 11
+    res = vs.similarity_search_with_score("seven 2", k=20, filter={"kind": "b"})
+    assert len(res) == 4 and all(r[0].metadata["kind"] == "b" and r[0].metadata["resource_hash"] == "def456" for r in res)
+    res = vs.similarity_search("seven 2", k=3, filter={"kind": "a", "n": 2})      # values compared as text
+    assert [d.page_content for d in res] == ["seven 2"]
+    assert res[0].metadata["display_name"] == "Seven" and res[0].metadata["url"] == "http://x/7"
+    assert vs.similarity_search("x", k=3, filter={"missing": "1"}) == []
+    # soft-deleted documents are hidden unless include_deleted (:304-308)
+    vs.register_document(8, is_deleted=True)
+    assert all(d.metadata["kind"] != "b" for d in vs.similarity_search("eight 1", k=11))
+    assert vs.similarity_search("eight 1", k=1, include_deleted=True)[0].page_content == "eight 1"
+    vs.register_document(8, is_deleted=False)
+    # delete by chunk id and by document id (:493-535)
+    assert vs.delete(ids=[ids8[0]]) is True and vs.count() == 10
+    assert vs.similarity_search("eight 0", k=1)[0].page_content != "eight 0"
+    assert vs.delete(document_id=7) is True and vs.count() == 4
+    assert vs.delete() is False
+    # upsert on (document_id, chunk_index) (:173-176)
+    vs.add_texts(["eight one, revised"], document_id=8)                            # replaces chunk_index 0? no: index 0 was deleted
+    vs.add_texts(["eight 1 v2", "eight 2 v2"], document_id=8)                      # indices 0,1 again -> replaces
+    texts = sorted(d.page_content for d in vs.similarity_search("eight", k=50))
+    assert "eight one, revised" not in texts and "eight 1 v2" in texts and "eight 1" not in texts
+    # metadata is never None (:560-581)
+    assert all(isinstance(d.metadata, dict) for d in vs.similarity_search("loose", k=50))
+
+
+def test_store_objects_share_the_collection(fresh_store):
+    from archi_b200 import B200VectorStore
+    emb = TableEmbeddings(32)
+    a = fresh_store("t_shared", emb=emb)
+    a.add_texts(["alpha", "beta"])
+    b = B200VectorStore(pg_config={}, embedding_function=emb, collection_name="t_shared")   # per-request construction
+    assert b.count() == 2 and b.similarity_search("beta", k=1)[0].page_content == "beta"
+    with pytest.raises(ValueError, match="metric is fixed"):
+        B200VectorStore(None, emb, "t_shared", "l2")
+
+
+def test_hybrid_search_matches_oracle(fresh_store):
+    from archi_b200 import HybridRetriever
+    emb = TableEmbeddings(128)
+    vs = fresh_store("t_hybrid", emb=emb)
+    texts = ["the detector measures muon momentum", "jets are clustered with anti-kt", "muon chambers and muon triggers",
+             "the trigger menu selects events", "grid computing sites run jobs", "muon", "tracker alignment constants"] * 3
+    texts = [f"{t} #{i}" for i, t in enumerate(texts)]
+    vs.add_texts(texts, metadatas=[{"i": i} for i in range(len(texts))])
+    query = "muon trigger"
+    corpus = np.asarray(emb.embed_documents(texts), dtype=np.float32)
+    q = np.asarray(emb.embed_query(query), dtype=np.float32)
+    bm = orc.bm25_scores([orc.tokenize(t) for t in texts], orc.tokenize(query))
+    for ws, wb in ((0.7, 0.3), (0.4, 0.6), (0.0, 1.0)):
+        res = vs.hybrid_search(query, k=6, semantic_weight=ws, bm25_weight=wb)
+        comb, ids = orc.exact_hybrid_topk("cosine", corpus, q, bm, ws, wb, 6)
+        assert [r[0].metadata["i"] for r in res] == ids.tolist()
+        assert np.allclose([r[1] for r in res], comb, rtol=1e-5, atol=2e-6)
+    r = HybridRetriever(vs, k=4, bm25_weight=0.6, semantic_weight=0.4)
+    got = r.invoke(query)
+    comb, ids = orc.exact_hybrid_topk("cosine", corpus, q, bm, 0.4, 0.6, 4)
+    assert [g[0].metadata["i"] for g in got] == ids.tolist()
+
+
+def test_hybrid_without_bm25_index_raises_and_retriever_reraises(fresh_store):
+    from archi_b200 import HybridRetriever
+    vs = fresh_store("t_nobm25", bm25_index=False)
+    vs.add_texts(["a b c", "d e f"])
+    with pytest.raises(RuntimeError, match="BM25 index"):           # :281-290
+        vs.hybrid_search("a", k=1)
+    with pytest.raises(RuntimeError, match="BM25 index"):           # hybrid_retriever.py:93-99
+        HybridRetriever(vs).invoke("a")
+
+
+def test_b200_embeddings_end_to_end(fresh_store):
+    import torch
+    from archi_b200 import B200Embeddings
+    emb = B200Embeddings(dtype="f32")
+    texts = ["The detector measures muon momentum.\nSecond line.", "Jets are clustered with anti-kt.", "short", "x " * 400]
+    vecs = np.asarray(emb.embed_documents(texts), dtype=np.float32)
+    assert vecs.shape == (4, 384)                                    # test_ingestion_pipeline_isolation.py:128-142
+    assert np.allclose(np.linalg.norm(vecs, axis=1), 1.0, atol=1e-5)
+    # the fused kernel equals torch's own mean-pool + normalise on the same hidden states
+    hidden, mask = emb._forward(emb._clean(texts))
+    m = mask.unsqueeze(-1).float()
+    ref = (hidden.float() * m).sum(1) / m.sum(1).clamp(min=1e-9)
+    ref = torch.nn.functional.normalize(ref, p=2, dim=1)
+    assert np.allclose(vecs, ref.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    vs = fresh_store("t_e2e", emb=emb)
+    vs.add_texts(texts)                                              # goes through pool_normalize_append
+    assert vs.count() == 4
+    assert np.allclose(vs.native.read_rows(0, 4), vecs, rtol=1e-5, atol=2e-6)
+    top = vs.similarity_search_with_score(texts[1], k=1)[0]
+    assert top[0].page_content == texts[1] and top[1] == pytest.approx(1.0, abs=1e-4)
