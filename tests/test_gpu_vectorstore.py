@@ -179,7 +179,7 @@ def test_filter_delete_upsert_and_document_metadata(fresh_store):
     assert vs.similarity_search("x", k=3, filter={"missing": "1"}) == []
     # soft-deleted documents are hidden unless include_deleted (:304-308)
     vs.register_document(8, is_deleted=True)
-    assert all(d.metadata["kind"] != "b" for d in vs.similarity_search("eight 1", k=11))
+    assert all(d.metadata.get("kind") != "b" for d in vs.similarity_search("eight 1", k=11))
     assert vs.similarity_search("eight 1", k=1, include_deleted=True)[0].page_content == "eight 1"
     vs.register_document(8, is_deleted=False)
     # delete by chunk id and by document id (:493-535)
