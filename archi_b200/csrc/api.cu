@@ -116,11 +116,8 @@ static int search_impl(archi_store *s, const float *queries, int queries_loc, in
     ARCHI_REQUIRE(nq == 0 || k == 0 || (out_scores && out_ids), "search: null outputs");
     ARCHI_REQUIRE(queries_loc == ARCHI_HOST || queries_loc == ARCHI_DEVICE, "search: bad queries_loc");
     ARCHI_REQUIRE(out_loc == ARCHI_HOST || out_loc == ARCHI_DEVICE, "search: bad out_loc");
-    if (path == ARCHI_PATH_TENSOR) {
-        set_error("search: the tensor-core path is not supported in this build");
-        return ARCHI_EUNSUPPORTED;
-    }
-    ARCHI_REQUIRE(path == ARCHI_PATH_AUTO || path == ARCHI_PATH_STREAM, "search: bad path %d", path);
+    ARCHI_REQUIRE(path == ARCHI_PATH_AUTO || path == ARCHI_PATH_STREAM || path == ARCHI_PATH_TENSOR,
+                  "search: bad path %d", path);
     if (nq == 0 || k == 0) return ARCHI_OK;
 
     std::lock_guard<std::mutex> lock(s->mu);
@@ -148,6 +145,18 @@ static int search_impl(archi_store *s, const float *queries, int queries_loc, in
         ARCHI_CUDA(cudaEventCreate(&s->ws.ev0));
         ARCHI_CUDA(cudaEventCreate(&s->ws.ev1));
     }
+    // ---- path selection: the tensor-core path needs a real batch, k <= 128 and no per-row bias ----
+    bool use_tensor = false;
+    if (path == ARCHI_PATH_TENSOR) {
+        if (hybrid || !tensor_path_supported(s, k)) {
+            set_error("search: the tensor-core path is not supported for this call (hybrid=%d, k=%d, rows=%lld)",
+                      hybrid, k, (long long)s->rows);
+            return ARCHI_EUNSUPPORTED;
+        }
+        use_tensor = true;
+    } else if (path == ARCHI_PATH_AUTO) {
+        use_tensor = !hybrid && nq >= kTensorMinBatch && tensor_path_supported(s, k);
+    }
 
     ScanArgs a;
     a.corpus = s->data;
@@ -164,8 +173,41 @@ static int search_impl(archi_store *s, const float *queries, int queries_loc, in
     a.w_bias = w_bias;
     a.bias_stride = s->rows;
 
-    int passes = 0, grid = 0;
+    int passes = 0, grid = 0, unverified_total = 0;
     double kernel_ms = 0.0;
+    if (use_tensor) {
+        std::vector<int> flags;
+        for (int q0 = 0; q0 < nq; q0 += kTensorMaxBatch) {
+            const int nb = nq - q0 < kTensorMaxBatch ? nq - q0 : kTensorMaxBatch;
+            int n_unv = 0;
+            double ms = 0.0;
+            flags.assign(nb, 0);
+            int rc = launch_tensor_search(s, q_dev + (size_t)q0 * s->dim, nb, k, filter_mask_dev, include_deleted,
+                                          o_scores + (size_t)q0 * k, o_ids + (size_t)q0 * k, id_offset, st, &n_unv,
+                                          flags.data(), &ms);
+            if (rc != ARCHI_OK) return rc;
+            kernel_ms += ms;
+            ++passes;
+            grid = s->stats.grid;
+            // queries whose exactness proof failed are answered by the exact streaming scan
+            for (int i = 0; n_unv > 0 && i < nb; ++i) {
+                if (!flags[i]) continue;
+                ++unverified_total;
+                a.nqb = 1;
+                a.k = k;
+                a.queries = q_dev + (size_t)(q0 + i) * s->dim;
+                a.bias = nullptr;
+                a.cursor_key = nullptr;
+                a.cursor_id = nullptr;
+                int g2 = 0;
+                rc = launch_scan(s, a, st, &g2);
+                if (rc != ARCHI_OK) return rc;
+                rc = launch_scan_finalize(s, a, g2, k, 0, o_scores + (size_t)(q0 + i) * k, o_ids + (size_t)(q0 + i) * k,
+                                          id_offset, nullptr, nullptr, st);
+                if (rc != ARCHI_OK) return rc;
+            }
+        }
+    } else {
     for (int q0 = 0; q0 < nq; q0 += kMaxQB) {
         a.nqb = nq - q0 < kMaxQB ? nq - q0 : kMaxQB;
         a.queries = q_dev + (size_t)q0 * s->dim;
@@ -192,10 +234,11 @@ static int search_impl(archi_store *s, const float *queries, int queries_loc, in
             ++passes;
         }
     }
-    s->stats.path = ARCHI_PATH_STREAM;
+    }
+    s->stats.path = use_tensor ? ARCHI_PATH_TENSOR : ARCHI_PATH_STREAM;
     s->stats.passes = passes;
     s->stats.grid = grid;
-    s->stats.unverified_queries = 0;
+    s->stats.unverified_queries = unverified_total;
     s->stats.last_kernel_ms = passes ? kernel_ms / passes : 0.0;
 
     if (out_loc == ARCHI_HOST) {
@@ -264,6 +307,7 @@ int archi_store_destroy(archi_store_t *s)
     if (s->norm2) cudaFree(s->norm2);
     if (s->alive) cudaFree(s->alive);
     free_workspace(s->ws);
+    free_tensor_workspace(s->tws);
     delete s;
     return ARCHI_OK;
 }
@@ -339,6 +383,7 @@ int archi_store_reset(archi_store_t *s)
     ARCHI_CUDA(cudaMemset(s->alive, 0, (size_t)((s->capacity + 31) / 32 + 1) * sizeof(uint32_t)));
     s->rows = 0;
     s->deleted = 0;
+    s->epoch++;
     return ARCHI_OK;
 }
 
@@ -380,6 +425,7 @@ int archi_store_append(archi_store_t *s, const void *rows, int src_dtype, int sr
     }
     if (rc != ARCHI_OK) return rc;
     s->rows += n;
+    s->epoch++;
     return ARCHI_OK;
 }
 
@@ -401,6 +447,7 @@ int archi_store_delete_rows(archi_store_t *s, const int64_t *rows_host, int64_t 
     if (rc == ARCHI_OK) {
         ARCHI_CUDA(cudaMemcpy(&changed, changed_dev, sizeof(int), cudaMemcpyDeviceToHost));
         s->deleted += changed;
+        s->epoch++;
     }
     cudaFree(rows_dev);
     cudaFree(changed_dev);
@@ -562,6 +609,7 @@ int archi_pool_normalize_append(archi_store_t *s, const void *hidden_dev, int hi
                                    reinterpret_cast<cudaStream_t>(stream));
     if (rc != ARCHI_OK) return rc;
     s->rows += B;
+    s->epoch++;
     return ARCHI_OK;
 }
 

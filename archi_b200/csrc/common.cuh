@@ -48,6 +48,8 @@ extern std::atomic<int64_t> g_launches;
 constexpr int kMaxListK = 128;     // entries a warp-register list holds (4 per lane)
 constexpr int kScanThreads = 256;  // 8 warps per CTA
 constexpr int kMaxQB = 8;          // queries per corpus pass on the streaming path
+constexpr int kTensorMinBatch = 9; // ARCHI_PATH_AUTO: batches at least this large take the tensor path
+constexpr int kTensorMaxBatch = 2048;  // queries per tensor-path launch (16 query tiles)
 
 struct Workspace {
     // per-CTA partial lists of the streaming scan: [grid][kMaxQB][kMaxListK]
@@ -63,6 +65,21 @@ struct Workspace {
     int64_t *out_ids = nullptr;
     int64_t out_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// scratch of the tensor-core path (tensor.cu)
+struct TensorWorkspace {
+    void *qstage = nullptr;      size_t qstage_bytes = 0;   // staged queries (bf16 / padded fp32)
+    void *qinfo = nullptr;       size_t qinfo_bytes = 0;
+    uint32_t *thr_g = nullptr;   size_t thr_bytes = 0;      // shared thresholds
+    int *unverified = nullptr;   size_t unv_bytes = 0;      // per-query flag + counter
+    void *cand = nullptr;        size_t cand_bytes = 0;     // [grid][128][cap] candidates
+    int *cand_cnt = nullptr;     size_t cnt_bytes = 0;
+    void *aux = nullptr;         size_t aux_bytes = 0;      // [capacity] (a, b) per row
+    float *max_norm2 = nullptr;
+    int64_t maxnorm_epoch = -1;
+    int64_t aux_epoch = -1;
+    bool aux_alive = false, aux_had_filter = false;
 };
 
 }  // namespace archi
@@ -83,6 +100,8 @@ struct archi_store {
     int timing = 0;
     archi_search_stats_t stats{};
     archi::Workspace ws;
+    archi::TensorWorkspace tws;
+    int64_t epoch = 0;        // bumped whenever rows / tombstones change (invalidates cached aux)
     std::mutex mu;
 };
 
@@ -134,6 +153,11 @@ int launch_pool_normalize(const void *hidden, int hidden_dtype, const void *mask
 int launch_bm25(const int32_t *doc_ids, const int32_t *tfs, int64_t n_post, float idf,
                 const float *doc_len, float avgdl, float k1, float b, float sign, float *out,
                 cudaStream_t st);
+int tensor_path_supported(const archi_store *s, int k);
+int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, const uint32_t *filter, int include_deleted,
+                         float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st,
+                         int *n_unverified_host, int *unverified_host, double *coarse_ms);
+void free_tensor_workspace(TensorWorkspace &w);
 int launch_merge_lists(const float *scores, const int64_t *ids, int n_lists, int nq, int k,
                        int larger_is_better, float *out_scores, int64_t *out_ids, cudaStream_t st);
 

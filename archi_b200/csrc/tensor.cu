@@ -1,0 +1,839 @@
+// tensor.cu -- the large-batch search path: TMA-fed tcgen05/TMEM coarse scorer with a fused
+// threshold filter, followed by an exact fp32 rescoring of the surviving candidates.
+//
+// Replaces the same reference statement as scan.cu (postgres_vectorstore.py:317-332 + :361) for
+// query batches where the scan is a real dense contraction.  No N x Q score matrix is written:
+//   1. tc_prep_kernel     stages the queries for the tensor pipe (bf16 copy for bf16 stores, padded
+//                         fp32 copy read as tf32 for fp32 stores) and computes, per query, a bound
+//                         eps on |coarse key - exact key|.
+//   2. tc_aux_kernel      per-row epilogue constants (a, b): key = dot * a + b  (cosine: a = 1/|c|;
+//                         l2: a = 2, b = -|c|^2; ip: a = 1); masked / deleted rows get b = -inf.
+//   3. tc_coarse_kernel   persistent warp-specialised GEMM.  One CTA per SM: warp 0 = TMA producer
+//                         (128B-swizzled tiles of 128 queries and 256 corpus rows through a 4-stage
+//                         mbarrier ring), warp 1 = tcgen05.mma issuer (M=128 queries x N=256 rows,
+//                         fp32 accumulators double-buffered in TMEM, 2 x 256 columns), warps 2-5 =
+//                         epilogue: tcgen05.ld the 128 x 256 scores, one query per thread, and keep
+//                         only keys above that query's running threshold in a per-(CTA, query)
+//                         candidate buffer; when a buffer fills, the owning warp selects its k' best
+//                         by a ballot/REDUX bisection on the key bits and raises the threshold
+//                         (shared between CTAs through an atomicMax word per query).
+//   4. tc_select_kernel   per query: union of the candidate buffers -> k' best coarse keys -> exact
+//                         fp32 rescoring against the stored rows -> top-k, plus the proof that no
+//                         rejected row can belong to the exact top-k:  e_k > T + eps.  Queries that
+//                         fail the proof are flagged and re-run on the exact streaming path.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "topk.cuh"
+
+namespace archi {
+namespace tc {
+
+constexpr int BM = 128;            // queries per tile (MMA M, TMEM lanes)
+constexpr int BN = 256;            // corpus rows per tile (MMA N, TMEM columns)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * 128;  // one 128-byte swizzle row per query per K chunk
+constexpr int B_BYTES = BN * 128;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int EPI_THREADS = 128;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_QT = 16;         // query tiles per launch (2048 queries)
+constexpr int SLOTS = 16;          // candidate entries per lane during a compaction (C <= 512)
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * BN * 8 + 256;
+
+// order-preserving map float -> uint32 (larger float <=> larger uint)
+__device__ __forceinline__ uint32_t fmap(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float funmap(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+// shared threshold word: 0 = "no threshold published yet"
+__device__ __forceinline__ float thr_from_word(uint32_t u) { return u ? funmap(u) : -CUDART_INF_F; }
+
+struct QInfo {
+    float rn_q;   // 1 / |q|
+    float qn2;    // |q|^2
+    float eps;    // bound on |coarse key - exact key| in coarse-key space
+    float pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// 1. query staging + error bound
+// ---------------------------------------------------------------------------------------------
+struct PrepParams {
+    const float *queries;  // [nq, dim]
+    int nq, dim, ldq;      // ldq: row stride of the staged copy, in elements
+    int tf32;              // 1: staged copy is fp32 (read as tf32), 0: bf16
+    int metric;
+    void *qstage;          // [nq_pad, ldq]
+    QInfo *qinfo;          // [nq]
+    uint32_t *thr_g;       // [nq] shared thresholds (mapped), reset to 0
+    int *unverified;       // [nq]
+    const float *max_norm2;// [1] max |row|^2 over the store
+};
+
+__global__ void __launch_bounds__(128) tc_prep_kernel(const PrepParams p)
+{
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ float s_a[4], s_b[4];
+    const float *src = p.queries + (size_t)q * p.dim;
+    float n2 = 0.f, e2 = 0.f;
+    for (int e = tid; e < p.ldq; e += 128) {
+        const float v = e < p.dim ? src[e] : 0.f;
+        n2 = fmaf(v, v, n2);
+        if (p.tf32) {
+            reinterpret_cast<float *>(p.qstage)[(size_t)q * p.ldq + e] = v;
+        } else {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            reinterpret_cast<__nv_bfloat16 *>(p.qstage)[(size_t)q * p.ldq + e] = h;
+            const float d = v - __bfloat162float(h);
+            e2 = fmaf(d, d, e2);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        n2 += __shfl_xor_sync(kFull, n2, d);
+        e2 += __shfl_xor_sync(kFull, e2, d);
+    }
+    if (lane == 0) {
+        s_a[warp] = n2;
+        s_b[warp] = e2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        n2 = s_a[0] + s_a[1] + s_a[2] + s_a[3];
+        e2 = s_b[0] + s_b[1] + s_b[2] + s_b[3];
+        const float qn = sqrtf(n2);
+        // |delta(q.c)| <= unit * |c| :  bf16 queries: |q - bf16(q)| (corpus is exact);
+        // tf32: both operands truncated to 10 mantissa bits -> 2^-9 (1 + 2^-11) |q|;
+        // plus fp32 accumulation slack dim * 2^-22 |q|.
+        float unit = p.tf32 ? 1.0005f * 0.001953125f * qn : sqrtf(e2) * 1.0001f;
+        unit += (float)p.dim * 2.4e-7f * qn;
+        const float maxn = sqrtf(*p.max_norm2);
+        float eps;
+        if (p.metric == ARCHI_COSINE) eps = unit;                 // key = dot / |c|
+        else if (p.metric == ARCHI_IP) eps = unit * maxn;         // key = dot
+        else eps = 2.f * unit * maxn + 1e-6f * maxn * maxn;       // key = 2 dot - |c|^2
+        QInfo qi;
+        qi.rn_q = n2 > 0.f ? 1.0f / qn : 0.f;
+        qi.qn2 = n2;
+        qi.eps = eps;
+        qi.pad = 0.f;
+        p.qinfo[q] = qi;
+        p.thr_g[q] = 0u;
+        p.unverified[q] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. per-row epilogue constants
+// ---------------------------------------------------------------------------------------------
+__global__ void tc_aux_kernel(float2 *aux, const float *norm2, const uint32_t *alive, const uint32_t *filter,
+                              long long n, int metric)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool ok = true;
+    if (alive) ok = ok && ((alive[i >> 5] >> (i & 31)) & 1u);
+    if (filter) ok = ok && ((filter[i >> 5] >> (i & 31)) & 1u);
+    const float n2 = norm2[i];
+    float2 ab;
+    if (metric == ARCHI_COSINE) {
+        ab = make_float2(n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f, 0.f);
+        if (!(n2 > 0.f)) ok = false;
+    } else if (metric == ARCHI_IP) {
+        ab = make_float2(1.f, 0.f);
+    } else {
+        ab = make_float2(2.f, -n2);
+    }
+    if (!ok) ab = make_float2(0.f, -CUDART_INF_F);
+    aux[i] = ab;
+}
+
+__global__ void tc_maxnorm_kernel(const float *norm2, long long n, float *out)
+{
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, norm2[i]);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. the coarse scorer
+// ---------------------------------------------------------------------------------------------
+struct CoarseParams {
+    long long n;          // corpus rows
+    int n_ctiles;         // ceil(n / BN)
+    int kchunks;          // ceil(ld / elements per 128 B)
+    int kelems;           // elements per 128-byte chunk (64 bf16, 32 fp32)
+    int nq;               // queries in this launch
+    int qt_count;         // query tiles
+    int ngroups;          // gridDim.x / qt_count
+    int kprime;           // candidates kept per compaction
+    int cap;              // entries per candidate buffer (C)
+    int exit_cap;         // buffers larger than this are compacted before the CTA exits
+    const float2 *aux;    // [n]
+    uint2 *cand;          // [grid][BM][cap]  (key bits, row id)
+    int *cand_cnt;        // [grid][BM]
+    uint32_t *thr_g;      // [nq]
+};
+
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
+{
+    // K-major, 128-byte swizzle: 8-row x 128 B atoms, 1024 B apart (SBO); LBO unused (1);
+    // descriptor version 1 (sm_100); layout type 2 = SWIZZLE_128B.
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Warp-collective: keep the kprime best entries of lane `owner`'s buffer (n entries, n <= 32*SLOTS),
+// return the new count and the new threshold (the kprime-th best key).
+__device__ __forceinline__ void compact_buffer(uint2 *buf, int n, int kprime, int lane, int &new_cnt, float &new_thr)
+{
+    uint32_t uk[SLOTS];
+    uint32_t id[SLOTS];
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) {
+        const int i = t * 32 + lane;
+        uk[t] = 0u;
+        id[t] = 0u;
+        if (i < n) {
+            const uint2 e = buf[i];
+            uk[t] = fmap(__uint_as_float(e.x));
+            id[t] = e.y;
+        }
+    }
+    // bisection on the mapped key bits: largest T with count(uk >= T) >= kprime
+    uint32_t T = 0u;
+#pragma unroll 1
+    for (int b = 31; b >= 0; --b) {
+        const uint32_t trial = T | (1u << b);
+        int c = 0;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) c += (uk[t] >= trial) ? 1 : 0;
+        c = __reduce_add_sync(kFull, c);
+        if (c >= kprime) T = trial;
+    }
+    // keep everything above T and only as many entries equal to T as are needed to reach kprime
+    // (dropping a row whose coarse key equals the new threshold is covered by the proof)
+    int c_gt = 0;
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) c_gt += (uk[t] > T) ? 1 : 0;
+    c_gt = __reduce_add_sync(kFull, c_gt);
+    int need_eq = kprime - c_gt;
+    int base = 0;
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) {
+        const bool valid = (t * 32 + lane) < n;
+        const bool gt = valid && uk[t] > T;
+        const bool eq = valid && uk[t] == T;
+        const unsigned m_eq = __ballot_sync(kFull, eq);
+        const bool keep = gt || (eq && __popc(m_eq & ((1u << lane) - 1u)) < need_eq);
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (keep) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            buf[pos] = make_uint2(__float_as_uint(funmap(uk[t])), id[t]);
+        }
+        base += __popc(m);
+        const int took_eq = __popc(m_eq);
+        need_eq -= took_eq < need_eq ? took_eq : need_eq;
+    }
+    new_cnt = base;
+    new_thr = funmap(T);
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                 const CoarseParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t raw = ptx::smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte aligned (128B swizzle atoms)
+    unsigned char *base_ptr = smem_dyn + (base - raw);
+    // layout: [STAGES x (A | B)] [aux 2 x BN float2] [barriers] [tmem ptr]
+    float2 *s_aux = reinterpret_cast<float2 *>(base_ptr + STAGES * STAGE_BYTES);
+    const uint32_t bar0 = base + STAGES * STAGE_BYTES + 2 * BN * 8;
+    const uint32_t full_bar = bar0, empty_bar = bar0 + 8 * STAGES;
+    const uint32_t tfull_bar = bar0 + 16 * STAGES, tempty_bar = tfull_bar + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + STAGES * STAGE_BYTES + 2 * BN * 8 + 16 * STAGES + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x % p.qt_count;
+    const int group = blockIdx.x / p.qt_count;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_c);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(full_bar + 8 * s, 1);
+            ptx::mbar_init(empty_bar + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(tfull_bar + 8 * a, 1);
+            ptx::mbar_init(tempty_bar + 8 * a, 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int ct = group; ct < p.n_ctiles; ct += p.ngroups) {
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+                    ptx::mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    ptx::tma_load_2d(sa, &tmap_q, full_bar + 8 * s, kc * p.kelems, qt * BM);
+                    ptx::tma_load_2d(sa + A_BYTES, &tmap_c, full_bar + 8 * s, kc * p.kelems, ct * BN);
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B bf16 (1) or tf32 (2), both K-major, N = 256, M = 128
+            const uint32_t fmt = TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            int s = 0, u = 0;
+            uint32_t ph = 0;
+            for (int ct = group; ct < p.n_ctiles; ct += p.ngroups, ++u) {
+                const int acc = u & 1;
+                const uint32_t aph = (uint32_t)(u >> 1) & 1u;
+                ptx::mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(full_bar + 8 * s, ph);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint64_t adesc = smem_desc_sw128(sa);
+                    const uint64_t bdesc = smem_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+                        if (TF32)
+                            ptx::mma_tf32(tmem_d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kc | k4) ? 1u : 0u);
+                        else
+                            ptx::mma_bf16(tmem_d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kc | k4) ? 1u : 0u);
+                    }
+                    ptx::tc_commit(empty_bar + 8 * s);  // smem stage reusable once these MMAs retire
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                ptx::tc_commit(tfull_bar + 8 * acc);    // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ================= epilogue: one query per thread =================
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int tq = quad * 32 + lane;              // query row inside the tile
+        const int q = qt * BM + tq;
+        const bool active = q < p.nq;
+        const int et = threadIdx.x - 64;              // 0..127 among epilogue threads
+        uint2 *buf = p.cand + ((size_t)blockIdx.x * BM + tq) * p.cap;
+        float thr = active ? -CUDART_INF_F : CUDART_INF_F;
+        int cnt = 0;
+        int u = 0;
+        for (int ct = group; ct < p.n_ctiles; ct += p.ngroups, ++u) {
+            const int acc = u & 1;
+            const uint32_t aph = (uint32_t)(u >> 1) & 1u;
+            // this tile's per-row constants, fetched while the MMAs run
+            const long long r0 = (long long)ct * BN + et, r1 = r0 + EPI_THREADS;
+            const float2 ab0 = r0 < p.n ? p.aux[r0] : make_float2(0.f, -CUDART_INF_F);
+            const float2 ab1 = r1 < p.n ? p.aux[r1] : make_float2(0.f, -CUDART_INF_F);
+            if (active) thr = fmaxf(thr, thr_from_word(__ldcg(p.thr_g + q)));
+            float2 *aux_t = s_aux + acc * BN;
+            aux_t[et] = ab0;
+            aux_t[et + EPI_THREADS] = ab1;
+            ptx::named_bar_sync(1, EPI_THREADS);
+
+            ptx::mbar_wait(tfull_bar + 8 * acc, aph);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t row_base = (uint32_t)ct * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(taddr + c * 32, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 ab = aux_t[c * 32 + j];
+                    const float key = fmaf(__uint_as_float(r[j]), ab.x, ab.y);
+                    if (key > thr && cnt < p.cap) {
+                        buf[cnt] = make_uint2(__float_as_uint(key), row_base + c * 32 + j);
+                        ++cnt;
+                    }
+                }
+            }
+            // accumulator drained: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
+
+            // buffers that could overflow on the next tile are compacted now (warp-collective)
+            unsigned need = __ballot_sync(kFull, cnt > p.cap - BN);
+            while (need) {
+                const int owner = __ffs(need) - 1;
+                need &= need - 1;
+                const int n_o = __shfl_sync(kFull, cnt, owner);
+                uint2 *buf_o = p.cand + ((size_t)blockIdx.x * BM + quad * 32 + owner) * p.cap;
+                int nc;
+                float nt;
+                compact_buffer(buf_o, n_o, p.kprime, lane, nc, nt);
+                if (lane == owner) {
+                    cnt = nc;
+                    thr = fmaxf(thr, nt);
+                    atomicMax(p.thr_g + q, fmap(thr));
+                }
+            }
+        }
+        // exit: bound the number of candidates the select kernel has to look at
+        unsigned need = __ballot_sync(kFull, cnt > p.exit_cap);
+        while (need) {
+            const int owner = __ffs(need) - 1;
+            need &= need - 1;
+            const int n_o = __shfl_sync(kFull, cnt, owner);
+            uint2 *buf_o = p.cand + ((size_t)blockIdx.x * BM + quad * 32 + owner) * p.cap;
+            int nc;
+            float nt;
+            compact_buffer(buf_o, n_o, p.kprime, lane, nc, nt);
+            if (lane == owner) {
+                cnt = nc;
+                thr = fmaxf(thr, nt);
+                atomicMax(p.thr_g + q, fmap(thr));
+            }
+        }
+        p.cand_cnt[(size_t)blockIdx.x * BM + tq] = active ? cnt : 0;
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. select k' best coarse candidates, rescore exactly, prove, write the outputs
+// ---------------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 256;
+constexpr int KEPT_MAX = 320;
+
+struct SelectParams {
+    const void *corpus;
+    int dtype, dim, ld, metric;
+    const float *norm2;
+    const float *queries;     // [nq, dim] fp32 originals
+    const QInfo *qinfo;
+    const uint2 *cand;
+    const int *cand_cnt;
+    const uint32_t *thr_g;
+    int qt_count, ngroups, cap;
+    int k, kprime;
+    float *out_scores;
+    long long *out_ids;
+    long long id_offset;
+    int *unverified;          // [nq] flag
+    int *n_unverified;        // [1] counter
+};
+
+__device__ __forceinline__ float row_elem(const void *corpus, int dtype, size_t idx)
+{
+    if (dtype == ARCHI_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(corpus)[idx]);
+    return reinterpret_cast<const float *>(corpus)[idx];
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
+{
+    extern __shared__ uint32_t s_keys[];            // mapped coarse keys of every candidate of this query
+    __shared__ int s_off[160];                      // per-group offsets (ngroups <= 148) + total
+    __shared__ int s_count;
+    __shared__ uint32_t s_T;
+    __shared__ int s_nk;
+    __shared__ uint32_t s_kid[KEPT_MAX];
+    __shared__ float s_kc[KEPT_MAX];                // coarse key of the kept candidates
+    __shared__ float s_ex[KEPT_MAX];                // exact key (coarse-key space)
+    __shared__ float s_sc[KEPT_MAX];                // output score
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qt = q / BM, tq = q % BM;
+
+    if (tid == 0) {
+        int acc = 0;
+        for (int g = 0; g < p.ngroups; ++g) {
+            s_off[g] = acc;
+            acc += p.cand_cnt[((size_t)(g * p.qt_count + qt)) * BM + tq];
+        }
+        s_off[p.ngroups] = acc;
+        s_nk = 0;
+    }
+    __syncthreads();
+    const int total = s_off[p.ngroups];
+    for (int g = 0; g < p.ngroups; ++g) {
+        const int n_g = s_off[g + 1] - s_off[g];
+        const uint2 *src = p.cand + ((size_t)(g * p.qt_count + qt) * BM + tq) * p.cap;
+        for (int i = tid; i < n_g; i += SEL_THREADS) s_keys[s_off[g] + i] = fmap(__uint_as_float(src[i].x));
+    }
+    __syncthreads();
+
+    // T = kprime-th largest mapped key (0 when there are at most kprime candidates)
+    uint32_t T = 0u;
+    if (total > p.kprime) {
+        for (int b = 31; b >= 0; --b) {
+            const uint32_t trial = T | (1u << b);
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+            int c = 0;
+            for (int i = tid; i < total; i += SEL_THREADS) c += (s_keys[i] >= trial) ? 1 : 0;
+            c = __reduce_add_sync(kFull, c);
+            if (lane == 0 && c) atomicAdd(&s_count, c);
+            __syncthreads();
+            if (s_count >= p.kprime) T = trial;
+            __syncthreads();
+        }
+    }
+    // gather the survivors (key >= T)
+    for (int g = 0; g < p.ngroups; ++g) {
+        const int n_g = s_off[g + 1] - s_off[g];
+        const uint2 *src = p.cand + ((size_t)(g * p.qt_count + qt) * BM + tq) * p.cap;
+        for (int i = tid; i < n_g; i += SEL_THREADS) {
+            if (s_keys[s_off[g] + i] >= T) {
+                const int slot = atomicAdd(&s_nk, 1);
+                if (slot < KEPT_MAX) {
+                    const uint2 e = src[i];
+                    s_kid[slot] = e.y;
+                    s_kc[slot] = __uint_as_float(e.x);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const bool overflow = s_nk > KEPT_MAX;          // more ties at T than we can hold: cannot prove
+    const int nk = overflow ? KEPT_MAX : s_nk;
+
+    // exact fp32 rescoring, one warp per candidate
+    const QInfo qi = p.qinfo[q];
+    const float *qv = p.queries + (size_t)q * p.dim;
+    for (int c = warp; c < nk; c += SEL_THREADS / 32) {
+        const size_t row = s_kid[c];
+        float acc = 0.f;
+        for (int e = lane; e < p.dim; e += 32) {
+            const float x = row_elem(p.corpus, p.dtype, row * p.ld + e);
+            const float y = qv[e];
+            if (p.metric == ARCHI_L2) {
+                const float d = x - y;
+                acc = fmaf(d, d, acc);
+            } else {
+                acc = fmaf(x, y, acc);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
+        if (lane == 0) {
+            float ex, sc;
+            if (p.metric == ARCHI_COSINE) {
+                const float n2 = p.norm2[row];
+                const float rn = n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f;
+                ex = acc * rn;                                       // coarse-key space: dot / |c|
+                sc = fminf(1.f, fmaxf(-1.f, acc * qi.rn_q * rn));
+            } else if (p.metric == ARCHI_IP) {
+                ex = acc;
+                sc = -acc;
+            } else {
+                ex = qi.qn2 - acc;                                   // 2 q.c - |c|^2 = |q|^2 - d^2
+                sc = sqrtf(fmaxf(acc, 0.f));
+            }
+            s_ex[c] = ex;
+            s_sc[c] = sc;
+        }
+    }
+    __syncthreads();
+
+    // rank by exact key (ties: lower id) and write the k best
+    float ek = -CUDART_INF_F;                         // exact key at rank k-1
+    for (int i = tid; i < nk; i += SEL_THREADS) {
+        const float mine = s_ex[i];
+        const int mid = (int)s_kid[i];
+        int rank = 0;
+        for (int j = 0; j < nk; ++j) rank += better(s_ex[j], (int)s_kid[j], mine, mid) ? 1 : 0;
+        if (rank < p.k) {
+            p.out_scores[(size_t)q * p.k + rank] = s_sc[i];
+            p.out_ids[(size_t)q * p.k + rank] = (long long)mid + p.id_offset;
+        }
+        if (rank == p.k - 1) ek = mine;
+    }
+    for (int r = nk + tid; r < p.k; r += SEL_THREADS) {
+        p.out_scores[(size_t)q * p.k + r] = CUDART_NAN_F;
+        p.out_ids[(size_t)q * p.k + r] = -1;
+    }
+    // proof: every row outside the kept set has coarse key <= Tv, hence exact key <= Tv + eps
+    __shared__ float s_ek;
+    if (tid == 0) s_ek = -CUDART_INF_F;
+    __syncthreads();
+    if (ek > -CUDART_INF_F) s_ek = ek;               // exactly one thread holds rank k-1
+    __syncthreads();
+    if (tid == 0) {
+        float Tv = total > p.kprime ? funmap(T) : -CUDART_INF_F;
+        Tv = fmaxf(Tv, thr_from_word(p.thr_g[q]));
+        bool ok = !overflow;
+        if (Tv > -CUDART_INF_F) ok = ok && nk >= p.k && s_ek > Tv + qi.eps;
+        if (!ok) {
+            p.unverified[q] = 1;
+            atomicAdd(p.n_unverified, 1);
+        }
+    }
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn()
+{
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(ptr);
+    }
+    return fn;
+}
+
+// [rows, ld] row-major matrix of 2- or 4-byte elements; box = 128 bytes x box_rows, 128B swizzle.
+static int make_tmap(CUtensorMap *map, const void *base, int is_f32, long long rows, int ld, int box_rows)
+{
+    encode_tiled_fn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ARCHI_ECUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)(rows > 0 ? rows : 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * (is_f32 ? 4u : 2u)};
+    const cuuint32_t box[2] = {(cuuint32_t)(is_f32 ? 32 : 64), (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld ld=%d)", (int)r, rows, ld);
+        return ARCHI_ECUDA;
+    }
+    return ARCHI_OK;
+}
+
+template <typename T>
+static int ensure_buf(T **ptr, size_t *cap_bytes, size_t need_bytes)
+{
+    if (*cap_bytes >= need_bytes && *ptr) return ARCHI_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap_bytes = 0;
+    ARCHI_CUDA(cudaMalloc(ptr, need_bytes));
+    *cap_bytes = need_bytes;
+    return ARCHI_OK;
+}
+
+int tensor_path_supported(const archi_store *s, int k)
+{
+    // row stride must be a whole number of 16-byte units (always true) and k' must fit a buffer
+    return s->rows > 0 && k >= 1 && k <= kMaxListK && s->rows < (1ll << 31);
+}
+
+int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, const uint32_t *filter, int include_deleted,
+                         float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st,
+                         int *n_unverified_host, int *unverified_host /* [nq] */, double *coarse_ms)
+{
+    using namespace tc;
+    TensorWorkspace &w = s->tws;
+    const bool tf32 = s->dtype == ARCHI_F32;
+    const int kelems = tf32 ? 32 : 64;
+    const int ldq = round_up(s->dim, tf32 ? 4 : 8);
+    const int qt_count = (nq + BM - 1) / BM;
+    ARCHI_REQUIRE(qt_count <= MAX_QT, "tensor path: at most %d queries per launch", MAX_QT * BM);
+    const int nq_pad = qt_count * BM;
+    int kprime = k <= 10 ? 32 : round_up(2 * k + 12, 32);
+    if (kprime > 256) kprime = 256;
+    const int cap = kprime + BN;
+    const int n_ctiles = (int)((s->rows + BN - 1) / BN);
+    int ngroups = s->sm_count / qt_count;
+    if (ngroups > 148) ngroups = 148;
+    if (ngroups < 1) ngroups = 1;
+    if (ngroups > n_ctiles) ngroups = n_ctiles;
+    const int grid = ngroups * qt_count;
+    int exit_cap = 40960 / ngroups;
+    if (exit_cap < kprime) exit_cap = kprime;
+    if (exit_cap > cap) exit_cap = cap;
+
+    // ---- workspace ----
+    int rc;
+    if ((rc = ensure_buf(&w.qstage, &w.qstage_bytes, (size_t)nq_pad * ldq * 4)) != ARCHI_OK) return rc;
+    if ((rc = ensure_buf(&w.qinfo, &w.qinfo_bytes, (size_t)nq_pad * sizeof(QInfo))) != ARCHI_OK) return rc;
+    if ((rc = ensure_buf(&w.thr_g, &w.thr_bytes, (size_t)nq_pad * 4)) != ARCHI_OK) return rc;
+    if ((rc = ensure_buf(&w.unverified, &w.unv_bytes, (size_t)(nq_pad + 1) * 4)) != ARCHI_OK) return rc;
+    if ((rc = ensure_buf(&w.cand, &w.cand_bytes, (size_t)grid * BM * cap * sizeof(uint2))) != ARCHI_OK) return rc;
+    if ((rc = ensure_buf(&w.cand_cnt, &w.cnt_bytes, (size_t)grid * BM * 4)) != ARCHI_OK) return rc;
+    {
+        void *before = w.aux;
+        if ((rc = ensure_buf(&w.aux, &w.aux_bytes, (size_t)s->capacity * sizeof(float2))) != ARCHI_OK) return rc;
+        if (w.aux != before) w.aux_epoch = -1;
+    }
+    if (!w.max_norm2) ARCHI_CUDA(cudaMalloc(&w.max_norm2, 4));
+
+    // ---- cached per-store data: max |row|^2 and the (a, b) constants ----
+    if (w.maxnorm_epoch != s->epoch) {
+        ARCHI_CUDA(cudaMemsetAsync(w.max_norm2, 0, 4, st));
+        tc_maxnorm_kernel<<<s->sm_count * 2, 256, 0, st>>>(s->norm2, s->rows, w.max_norm2);
+        ARCHI_CHECK_LAUNCH();
+        w.maxnorm_epoch = s->epoch;
+    }
+    const uint32_t *alive = include_deleted ? nullptr : s->alive;
+    const bool aux_cached = w.aux_epoch == s->epoch && w.aux_alive == (alive != nullptr) && filter == nullptr &&
+                            !w.aux_had_filter;
+    if (!aux_cached) {
+        tc_aux_kernel<<<(unsigned)((s->rows + 255) / 256), 256, 0, st>>>(reinterpret_cast<float2 *>(w.aux), s->norm2, alive,
+                                                                        filter, s->rows, s->metric);
+        ARCHI_CHECK_LAUNCH();
+        w.aux_epoch = s->epoch;
+        w.aux_alive = alive != nullptr;
+        w.aux_had_filter = filter != nullptr;
+    }
+
+    // ---- 1. stage queries ----
+    if (nq_pad > nq)  // padded query rows must be finite (zeros) for the MMA
+        ARCHI_CUDA(cudaMemsetAsync((char *)w.qstage + (size_t)nq * ldq * (tf32 ? 4 : 2), 0,
+                                   (size_t)(nq_pad - nq) * ldq * (tf32 ? 4 : 2), st));
+    PrepParams pp;
+    pp.queries = q_dev;
+    pp.nq = nq;
+    pp.dim = s->dim;
+    pp.ldq = ldq;
+    pp.tf32 = tf32;
+    pp.metric = s->metric;
+    pp.qstage = w.qstage;
+    pp.qinfo = reinterpret_cast<QInfo *>(w.qinfo);
+    pp.thr_g = w.thr_g;
+    pp.unverified = w.unverified;
+    pp.max_norm2 = w.max_norm2;
+    ARCHI_CUDA(cudaMemsetAsync(w.unverified + nq_pad, 0, 4, st));
+    tc_prep_kernel<<<nq, 128, 0, st>>>(pp);
+    ARCHI_CHECK_LAUNCH();
+
+    // ---- 3. coarse scorer ----
+    CUtensorMap tmap_q, tmap_c;
+    if ((rc = make_tmap(&tmap_q, w.qstage, tf32, nq_pad, ldq, BM)) != ARCHI_OK) return rc;
+    if ((rc = make_tmap(&tmap_c, s->data, tf32, s->rows, s->ld, BN)) != ARCHI_OK) return rc;
+    CoarseParams cp;
+    cp.n = s->rows;
+    cp.n_ctiles = n_ctiles;
+    cp.kchunks = (s->ld + kelems - 1) / kelems;
+    cp.kelems = kelems;
+    cp.nq = nq;
+    cp.qt_count = qt_count;
+    cp.ngroups = ngroups;
+    cp.kprime = kprime;
+    cp.cap = cap;
+    cp.exit_cap = exit_cap;
+    cp.aux = reinterpret_cast<const float2 *>(w.aux);
+    cp.cand = reinterpret_cast<uint2 *>(w.cand);
+    cp.cand_cnt = w.cand_cnt;
+    cp.thr_g = w.thr_g;
+    auto kern = tf32 ? tc_coarse_kernel<true> : tc_coarse_kernel<false>;
+    ARCHI_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    if (s->timing) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmap_q, tmap_c, cp);
+    ARCHI_CHECK_LAUNCH();
+    if (s->timing) {
+        ARCHI_CUDA(cudaEventRecord(s->ws.ev1, st));
+        ARCHI_CUDA(cudaEventSynchronize(s->ws.ev1));
+        float ms = 0.f;
+        ARCHI_CUDA(cudaEventElapsedTime(&ms, s->ws.ev0, s->ws.ev1));
+        *coarse_ms = ms;
+    }
+
+    // ---- 4. select + rescore + proof ----
+    SelectParams sp;
+    sp.corpus = s->data;
+    sp.dtype = s->dtype;
+    sp.dim = s->dim;
+    sp.ld = s->ld;
+    sp.metric = s->metric;
+    sp.norm2 = s->norm2;
+    sp.queries = q_dev;
+    sp.qinfo = reinterpret_cast<const QInfo *>(w.qinfo);
+    sp.cand = reinterpret_cast<const uint2 *>(w.cand);
+    sp.cand_cnt = w.cand_cnt;
+    sp.thr_g = w.thr_g;
+    sp.qt_count = qt_count;
+    sp.ngroups = ngroups;
+    sp.cap = cap;
+    sp.k = k;
+    sp.kprime = kprime;
+    sp.out_scores = out_scores;
+    sp.out_ids = reinterpret_cast<long long *>(out_ids);
+    sp.id_offset = id_offset;
+    sp.unverified = w.unverified;
+    sp.n_unverified = w.unverified + nq_pad;
+    const size_t sel_smem = (size_t)ngroups * exit_cap * 4;
+    ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sel_smem > 200 * 1024 ? 200 * 1024 : sel_smem)));
+    ARCHI_REQUIRE(sel_smem <= 200 * 1024, "tensor path: select kernel needs %zu B of shared memory", sel_smem);
+    tc_select_kernel<<<nq, SEL_THREADS, sel_smem, st>>>(sp);
+    ARCHI_CHECK_LAUNCH();
+
+    // ---- the proof's verdict (4 bytes + flags) ----
+    ARCHI_CUDA(cudaMemcpyAsync(n_unverified_host, w.unverified + nq_pad, 4, cudaMemcpyDeviceToHost, st));
+    ARCHI_CUDA(cudaStreamSynchronize(st));
+    if (*n_unverified_host > 0)
+        ARCHI_CUDA(cudaMemcpy(unverified_host, w.unverified, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    s->stats.grid = grid;
+    return ARCHI_OK;
+}
+
+void free_tensor_workspace(TensorWorkspace &w)
+{
+    void *ptrs[] = {w.qstage, w.qinfo, w.thr_g, w.unverified, w.cand, w.cand_cnt, w.aux, w.max_norm2};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    w = TensorWorkspace();
+}
+
+}  // namespace archi
