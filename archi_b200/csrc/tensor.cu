@@ -40,7 +40,6 @@ constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogu
 constexpr int EPI_THREADS = 128;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_QT = 16;         // query tiles per launch (2048 queries)
-constexpr int SLOTS = 16;          // candidate entries per lane during a compaction (C <= 512)
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * BN * 8 + 256;
 
 // order-preserving map float -> uint32 (larger float <=> larger uint)
@@ -200,7 +199,8 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
 }
 
 // Warp-collective: keep the kprime best entries of lane `owner`'s buffer (n entries, n <= 32*SLOTS),
-// return the new count and the new threshold (the kprime-th best key).
+// return the new count and the new threshold (a key T with exactly/at least kprime entries >= T).
+template <int SLOTS>
 __device__ __forceinline__ void compact_buffer(uint2 *buf, int n, int kprime, int lane, int &new_cnt, float &new_thr)
 {
     uint32_t uk[SLOTS];
@@ -226,6 +226,7 @@ __device__ __forceinline__ void compact_buffer(uint2 *buf, int n, int kprime, in
         for (int t = 0; t < SLOTS; ++t) c += (uk[t] >= trial) ? 1 : 0;
         c = __reduce_add_sync(kFull, c);
         if (c >= kprime) T = trial;
+        if (c == kprime) break;  // exactly kprime entries are >= T: T is already a valid threshold
     }
     // keep everything above T and only as many entries equal to T as are needed to reach kprime
     // (dropping a row whose coarse key equals the new threshold is covered by the proof)
@@ -253,6 +254,12 @@ __device__ __forceinline__ void compact_buffer(uint2 *buf, int n, int kprime, in
     }
     new_cnt = base;
     new_thr = funmap(T);
+}
+
+__device__ __forceinline__ void compact_dispatch(uint2 *buf, int n, int kprime, int cap, int lane, int &nc, float &nt)
+{
+    if (cap <= 512) compact_buffer<16>(buf, n, kprime, lane, nc, nt);
+    else compact_buffer<32>(buf, n, kprime, lane, nc, nt);
 }
 
 template <bool TF32>
@@ -403,7 +410,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
 
             // buffers that could overflow on the next tile are compacted now (warp-collective)
-            unsigned need = __ballot_sync(kFull, cnt > p.cap - BN);
+            unsigned need = __ballot_sync(kFull, cnt >= p.cap - BN);
             while (need) {
                 const int owner = __ffs(need) - 1;
                 need &= need - 1;
@@ -411,7 +418,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 uint2 *buf_o = p.cand + ((size_t)blockIdx.x * BM + quad * 32 + owner) * p.cap;
                 int nc;
                 float nt;
-                compact_buffer(buf_o, n_o, p.kprime, lane, nc, nt);
+                compact_dispatch(buf_o, n_o, p.kprime, p.cap, lane, nc, nt);
                 if (lane == owner) {
                     cnt = nc;
                     thr = fmaxf(thr, nt);
@@ -428,7 +435,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             uint2 *buf_o = p.cand + ((size_t)blockIdx.x * BM + quad * 32 + owner) * p.cap;
             int nc;
             float nt;
-            compact_buffer(buf_o, n_o, p.kprime, lane, nc, nt);
+            compact_dispatch(buf_o, n_o, p.kprime, p.cap, lane, nc, nt);
             if (lane == owner) {
                 cnt = nc;
                 thr = fmaxf(thr, nt);
@@ -692,7 +699,9 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     const int nq_pad = qt_count * BM;
     int kprime = k <= 10 ? 32 : round_up(2 * k + 12, 32);
     if (kprime > 256) kprime = 256;
-    const int cap = kprime + BN;
+    // buffer capacity: after a compaction (kprime entries) a buffer absorbs cap - BN - kprime more
+    // candidates before the next one; a whole tile (BN) always fits
+    const int cap = kprime <= 128 ? 512 : 1024;
     const int n_ctiles = (int)((s->rows + BN - 1) / BN);
     int ngroups = s->sm_count / qt_count;
     if (ngroups > 148) ngroups = 148;
