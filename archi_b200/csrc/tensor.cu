@@ -40,7 +40,8 @@ constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogu
 constexpr int EPI_THREADS = 128;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_QT = 16;         // query tiles per launch (2048 queries)
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * BN * 8 + 256;
+constexpr int DUMP_BYTES = EPI_THREADS * 32 * 4;  // one 32-float row per epilogue thread
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * BN * 8 + 256 + DUMP_BYTES;
 
 // order-preserving map float -> uint32 (larger float <=> larger uint)
 __device__ __forceinline__ uint32_t fmap(float f)
@@ -178,6 +179,7 @@ struct CoarseParams {
     int ngroups;          // gridDim.x / qt_count
     int kprime;           // candidates kept per compaction
     int cap;              // entries per candidate buffer (C)
+    int trigger;          // a buffer holding at least this many entries is compacted after the tile
     int exit_cap;         // buffers larger than this are compacted before the CTA exits
     const float2 *aux;    // [n]
     uint2 *cand;          // [grid][BM][cap]  (key bits, row id)
@@ -258,7 +260,11 @@ __device__ __forceinline__ void compact_buffer(uint2 *buf, int n, int kprime, in
 
 __device__ __forceinline__ void compact_dispatch(uint2 *buf, int n, int kprime, int cap, int lane, int &nc, float &nt)
 {
-    if (cap <= 512) compact_buffer<16>(buf, n, kprime, lane, nc, nt);
+    (void)cap;
+    if (n <= 64) compact_buffer<2>(buf, n, kprime, lane, nc, nt);
+    else if (n <= 128) compact_buffer<4>(buf, n, kprime, lane, nc, nt);
+    else if (n <= 256) compact_buffer<8>(buf, n, kprime, lane, nc, nt);
+    else if (n <= 512) compact_buffer<16>(buf, n, kprime, lane, nc, nt);
     else compact_buffer<32>(buf, n, kprime, lane, nc, nt);
 }
 
@@ -271,12 +277,13 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t raw = ptx::smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte aligned (128B swizzle atoms)
     unsigned char *base_ptr = smem_dyn + (base - raw);
-    // layout: [STAGES x (A | B)] [aux 2 x BN float2] [barriers] [tmem ptr]
+    // layout: [STAGES x (A | B)] [aux 2 x BN float2] [barriers, tmem ptr: 256 B] [key dump 16 KB]
     float2 *s_aux = reinterpret_cast<float2 *>(base_ptr + STAGES * STAGE_BYTES);
     const uint32_t bar0 = base + STAGES * STAGE_BYTES + 2 * BN * 8;
     const uint32_t full_bar = bar0, empty_bar = bar0 + 8 * STAGES;
     const uint32_t tfull_bar = bar0 + 16 * STAGES, tempty_bar = tfull_bar + 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + STAGES * STAGE_BYTES + 2 * BN * 8 + 16 * STAGES + 32);
+    float *s_dump = reinterpret_cast<float *>(base_ptr + STAGES * STAGE_BYTES + 2 * BN * 8 + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x % p.qt_count;
@@ -394,13 +401,31 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(taddr + c * 32, r);
                 ptx::tmem_ld_wait();
+                // branch-free pass: keys replace the raw dots, one mask bit per admitted column
+                uint32_t mask = 0u;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float2 ab = aux_t[c * 32 + j];
                     const float key = fmaf(__uint_as_float(r[j]), ab.x, ab.y);
-                    if (key > thr && cnt < p.cap) {
-                        buf[cnt] = make_uint2(__float_as_uint(key), row_base + c * 32 + j);
-                        ++cnt;
+                    r[j] = __float_as_uint(key);
+                    mask |= (key > thr) ? (1u << j) : 0u;
+                }
+                if (mask) {
+                    // rare path: park the 32 keys in this thread's shared-memory row so that the
+                    // admitted ones can be fetched by (dynamic) column index
+                    float4 *mine = reinterpret_cast<float4 *>(s_dump) + et;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        mine[j4 * EPI_THREADS] = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
+                                                             __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float key = s_dump[((j >> 2) * EPI_THREADS + et) * 4 + (j & 3)];
+                        if (cnt < p.cap) {
+                            buf[cnt] = make_uint2(__float_as_uint(key), row_base + c * 32 + j);
+                            ++cnt;
+                        }
                     }
                 }
             }
@@ -410,7 +435,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
 
             // buffers that could overflow on the next tile are compacted now (warp-collective)
-            unsigned need = __ballot_sync(kFull, cnt >= p.cap - BN);
+            unsigned need = __ballot_sync(kFull, cnt >= p.trigger);
             while (need) {
                 const int owner = __ffs(need) - 1;
                 need &= need - 1;
@@ -780,6 +805,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     cp.ngroups = ngroups;
     cp.kprime = kprime;
     cp.cap = cap;
+    cp.trigger = (cap - BN) < 2 * kprime ? (cap - BN) : 2 * kprime;
     cp.exit_cap = exit_cap;
     cp.aux = reinterpret_cast<const float2 *>(w.aux);
     cp.cand = reinterpret_cast<uint2 *>(w.cand);
