@@ -136,6 +136,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// One column for the 32 lanes of the warp's quadrant (address is warp-uniform); waits for the data.
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr)
+{
+    uint32_t v;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v)
+        : "r"(taddr)
+        : "memory");
+    return v;
+}
 __device__ __forceinline__ void tmem_ld_wait()
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");

@@ -22,6 +22,7 @@
 //                         rejected row can belong to the exact top-k:  e_k > T + eps.  Queries that
 //                         fail the proof are flagged and re-run on the exact streaming path.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -36,12 +37,12 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * 128;  // one 128-byte swizzle row per query per K chunk
 constexpr int B_BYTES = BN * 128;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int EPI_THREADS = 128;
+constexpr int NTHREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..5 / 6..9 epilogue groups 0 / 1
+constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_QT = 16;         // query tiles per launch (2048 queries)
-constexpr int DUMP_BYTES = EPI_THREADS * 32 * 4;  // one 32-float row per epilogue thread
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * BN * 8 + 256 + DUMP_BYTES;
+constexpr int AUX_BYTES = EPI_WARPS * BN * 8;       // a private (a, b) tile copy per epilogue warp
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + AUX_BYTES + 256;
 
 // order-preserving map float -> uint32 (larger float <=> larger uint)
 __device__ __forceinline__ uint32_t fmap(float f)
@@ -180,6 +181,7 @@ struct CoarseParams {
     int kprime;           // candidates kept per compaction
     int cap;              // entries per candidate buffer (C)
     int trigger;          // a buffer holding at least this many entries is compacted after the tile
+    int debug;            // profiling aid (ARCHI_TC_DEBUG): 1 = skip the MMAs, 2 = skip the epilogue math
     int exit_cap;         // buffers larger than this are compacted before the CTA exits
     const float2 *aux;    // [n]
     uint2 *cand;          // [grid][BM][cap]  (key bits, row id)
@@ -277,13 +279,12 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t raw = ptx::smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte aligned (128B swizzle atoms)
     unsigned char *base_ptr = smem_dyn + (base - raw);
-    // layout: [STAGES x (A | B)] [aux 2 x BN float2] [barriers, tmem ptr: 256 B] [key dump 16 KB]
+    // layout: [STAGES x (A | B)] [aux: EPI_WARPS x BN float2] [barriers, tmem ptr: 256 B]
     float2 *s_aux = reinterpret_cast<float2 *>(base_ptr + STAGES * STAGE_BYTES);
-    const uint32_t bar0 = base + STAGES * STAGE_BYTES + 2 * BN * 8;
+    const uint32_t bar0 = base + STAGES * STAGE_BYTES + AUX_BYTES;
     const uint32_t full_bar = bar0, empty_bar = bar0 + 8 * STAGES;
     const uint32_t tfull_bar = bar0 + 16 * STAGES, tempty_bar = tfull_bar + 16;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + STAGES * STAGE_BYTES + 2 * BN * 8 + 16 * STAGES + 32);
-    float *s_dump = reinterpret_cast<float *>(base_ptr + STAGES * STAGE_BYTES + 2 * BN * 8 + 256);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + STAGES * STAGE_BYTES + AUX_BYTES + 16 * STAGES + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x % p.qt_count;
@@ -353,6 +354,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     const uint64_t bdesc = smem_desc_sw128(sa + A_BYTES);
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
+                        if (p.debug & 1) break;
                         // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
                         if (TF32)
                             ptx::mma_tf32(tmem_d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kc | k4) ? 1u : 0u);
@@ -370,77 +372,84 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
     } else {
         // ================= epilogue: one query per thread =================
-        const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
-        const int tq = quad * 32 + lane;              // query row inside the tile
+        // Two groups of four warps; group g drains accumulator g (tiles u = g, g+2, ...), so each
+        // group has two MMA tile periods per tile.  Within a group, warp (warp & 3) owns that TMEM
+        // lane quadrant and thread `lane` owns query tq = quad*32 + lane.  Candidate bookkeeping is
+        // per (CTA, group, query): the two groups behave like two virtual CTAs.
+        const int grp = (warp - 2) >> 2;
+        const int quad = warp & 3;
+        const int tq = quad * 32 + lane;
         const int q = qt * BM + tq;
         const bool active = q < p.nq;
-        const int et = threadIdx.x - 64;              // 0..127 among epilogue threads
-        uint2 *buf = p.cand + ((size_t)blockIdx.x * BM + tq) * p.cap;
+        const size_t vcta = (size_t)blockIdx.x * 2 + grp;
+        uint2 *buf = p.cand + (vcta * BM + tq) * p.cap;
+        float2 *aux_w = s_aux + (warp - 2) * BN;         // this warp's private copy of the tile's (a, b)
         float thr = active ? -CUDART_INF_F : CUDART_INF_F;
         int cnt = 0;
-        int u = 0;
-        for (int ct = group; ct < p.n_ctiles; ct += p.ngroups, ++u) {
-            const int acc = u & 1;
+        int u = grp;
+        for (int ct = group + grp * p.ngroups; ct < p.n_ctiles; ct += 2 * p.ngroups, u += 2) {
             const uint32_t aph = (uint32_t)(u >> 1) & 1u;
-            // this tile's per-row constants, fetched while the MMAs run
-            const long long r0 = (long long)ct * BN + et, r1 = r0 + EPI_THREADS;
-            const float2 ab0 = r0 < p.n ? p.aux[r0] : make_float2(0.f, -CUDART_INF_F);
-            const float2 ab1 = r1 < p.n ? p.aux[r1] : make_float2(0.f, -CUDART_INF_F);
+            // this tile's per-row constants, fetched while the MMAs run (warp-private: no CTA barrier)
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) {
+                const long long r = (long long)ct * BN + i * 32 + lane;
+                aux_w[i * 32 + lane] = r < p.n ? __ldg(p.aux + r) : make_float2(0.f, -CUDART_INF_F);
+            }
             if (active) thr = fmaxf(thr, thr_from_word(__ldcg(p.thr_g + q)));
-            float2 *aux_t = s_aux + acc * BN;
-            aux_t[et] = ab0;
-            aux_t[et + EPI_THREADS] = ab1;
-            ptx::named_bar_sync(1, EPI_THREADS);
+            __syncwarp();
 
-            ptx::mbar_wait(tfull_bar + 8 * acc, aph);
+            ptx::mbar_wait(tfull_bar + 8 * grp, aph);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BN);
             const uint32_t row_base = (uint32_t)ct * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(taddr + c * 32, r);
-                ptx::tmem_ld_wait();
-                // branch-free pass: keys replace the raw dots, one mask bit per admitted column
-                uint32_t mask = 0u;
+
+            // one 32-column chunk, fully predicated (no branches, no slow path): a column whose key
+            // beats the threshold is stored at buf[cnt] by a predicated st.global and bumps cnt
+            auto process = [&](uint32_t (&r)[32], int c) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float2 ab = aux_t[c * 32 + j];
+                    const float2 ab = aux_w[c * 32 + j];
                     const float key = fmaf(__uint_as_float(r[j]), ab.x, ab.y);
-                    r[j] = __float_as_uint(key);
-                    mask |= (key > thr) ? (1u << j) : 0u;
+                    uint32_t took;
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p;\n\t"
+                        "setp.gt.f32 p, %2, %3;\n\t"
+                        "setp.lt.and.s32 p, %4, %5, p;\n\t"
+                        "@p st.global.v2.b32 [%1], {%6, %7};\n\t"
+                        "selp.u32 %0, 1, 0, p;\n\t"
+                        "}"
+                        : "=r"(took)
+                        : "l"(buf + cnt), "f"(key), "f"(thr), "r"(cnt), "r"(p.cap), "r"(__float_as_uint(key)),
+                          "r"(row_base + c * 32 + j)
+                        : "memory");
+                    cnt += (int)took;
                 }
-                if (mask) {
-                    // rare path: park the 32 keys in this thread's shared-memory row so that the
-                    // admitted ones can be fetched by (dynamic) column index
-                    float4 *mine = reinterpret_cast<float4 *>(s_dump) + et;
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4)
-                        mine[j4 * EPI_THREADS] = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
-                                                             __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
-                    while (mask) {
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float key = s_dump[((j >> 2) * EPI_THREADS + et) * 4 + (j & 3)];
-                        if (cnt < p.cap) {
-                            buf[cnt] = make_uint2(__float_as_uint(key), row_base + c * 32 + j);
-                            ++cnt;
-                        }
-                    }
-                }
+            };
+            uint32_t ra[32], rb[32];
+            ptx::tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+            for (int c = 0; c < ((p.debug & 2) ? 0 : BN / 32); c += 2) {
+                ptx::tmem_ld_wait();
+                ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);      // next chunk in flight
+                process(ra, c);
+                ptx::tmem_ld_wait();
+                if (c + 2 < BN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+                process(rb, c + 1);
             }
             // accumulator drained: hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
+            if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * grp);
 
-            // buffers that could overflow on the next tile are compacted now (warp-collective)
+            // eager compaction keeps the thresholds tight (warp-collective, one owner lane at a time)
             unsigned need = __ballot_sync(kFull, cnt >= p.trigger);
             while (need) {
                 const int owner = __ffs(need) - 1;
                 need &= need - 1;
                 const int n_o = __shfl_sync(kFull, cnt, owner);
-                uint2 *buf_o = p.cand + ((size_t)blockIdx.x * BM + quad * 32 + owner) * p.cap;
+                uint2 *buf_o = p.cand + (vcta * BM + quad * 32 + owner) * p.cap;
                 int nc;
                 float nt;
                 compact_dispatch(buf_o, n_o, p.kprime, p.cap, lane, nc, nt);
@@ -457,7 +466,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int owner = __ffs(need) - 1;
             need &= need - 1;
             const int n_o = __shfl_sync(kFull, cnt, owner);
-            uint2 *buf_o = p.cand + ((size_t)blockIdx.x * BM + quad * 32 + owner) * p.cap;
+            uint2 *buf_o = p.cand + (vcta * BM + quad * 32 + owner) * p.cap;
             int nc;
             float nt;
             compact_dispatch(buf_o, n_o, p.kprime, p.cap, lane, nc, nt);
@@ -467,7 +476,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 atomicMax(p.thr_g + q, fmap(thr));
             }
         }
-        p.cand_cnt[(size_t)blockIdx.x * BM + tq] = active ? cnt : 0;
+        p.cand_cnt[vcta * BM + tq] = active ? cnt : 0;
     }
 
     ptx::tc_fence_before();
@@ -511,7 +520,7 @@ __device__ __forceinline__ float row_elem(const void *corpus, int dtype, size_t 
 __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
 {
     extern __shared__ uint32_t s_keys[];            // mapped coarse keys of every candidate of this query
-    __shared__ int s_off[160];                      // per-group offsets (ngroups <= 148) + total
+    __shared__ int s_off[320];                      // per-list offsets (2 * ngroups <= 296) + total
     __shared__ int s_count;
     __shared__ uint32_t s_T;
     __shared__ int s_nk;
@@ -521,21 +530,24 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     __shared__ float s_sc[KEPT_MAX];                // output score
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qt = q / BM, tq = q % BM;
+    // candidate lists of this query: one per (CTA of its query tile, epilogue group)
+    const int nlists = 2 * p.ngroups;
+    auto list_base = [&](int l) { return ((size_t)((l >> 1) * p.qt_count + qt)) * 2 + (l & 1); };
 
     if (tid == 0) {
         int acc = 0;
-        for (int g = 0; g < p.ngroups; ++g) {
-            s_off[g] = acc;
-            acc += p.cand_cnt[((size_t)(g * p.qt_count + qt)) * BM + tq];
+        for (int l = 0; l < nlists; ++l) {
+            s_off[l] = acc;
+            acc += p.cand_cnt[list_base(l) * BM + tq];
         }
-        s_off[p.ngroups] = acc;
+        s_off[nlists] = acc;
         s_nk = 0;
     }
     __syncthreads();
-    const int total = s_off[p.ngroups];
-    for (int g = 0; g < p.ngroups; ++g) {
+    const int total = s_off[nlists];
+    for (int g = 0; g < nlists; ++g) {
         const int n_g = s_off[g + 1] - s_off[g];
-        const uint2 *src = p.cand + ((size_t)(g * p.qt_count + qt) * BM + tq) * p.cap;
+        const uint2 *src = p.cand + (list_base(g) * BM + tq) * p.cap;
         for (int i = tid; i < n_g; i += SEL_THREADS) s_keys[s_off[g] + i] = fmap(__uint_as_float(src[i].x));
     }
     __syncthreads();
@@ -557,9 +569,9 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
         }
     }
     // gather the survivors (key >= T)
-    for (int g = 0; g < p.ngroups; ++g) {
+    for (int g = 0; g < nlists; ++g) {
         const int n_g = s_off[g + 1] - s_off[g];
-        const uint2 *src = p.cand + ((size_t)(g * p.qt_count + qt) * BM + tq) * p.cap;
+        const uint2 *src = p.cand + (list_base(g) * BM + tq) * p.cap;
         for (int i = tid; i < n_g; i += SEL_THREADS) {
             if (s_keys[s_off[g] + i] >= T) {
                 const int slot = atomicAdd(&s_nk, 1);
@@ -732,8 +744,11 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     if (ngroups > 148) ngroups = 148;
     if (ngroups < 1) ngroups = 1;
     if (ngroups > n_ctiles) ngroups = n_ctiles;
+    // the select kernel keeps every surviving candidate key of one query in shared memory
+    // (2 lists per CTA of the query's tile, at least kprime entries each)
+    if (2 * ngroups * kprime > 49152) ngroups = 49152 / (2 * kprime);
     const int grid = ngroups * qt_count;
-    int exit_cap = 40960 / ngroups;
+    int exit_cap = 49152 / (2 * ngroups);
     if (exit_cap < kprime) exit_cap = kprime;
     if (exit_cap > cap) exit_cap = cap;
 
@@ -743,8 +758,8 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     if ((rc = ensure_buf(&w.qinfo, &w.qinfo_bytes, (size_t)nq_pad * sizeof(QInfo))) != ARCHI_OK) return rc;
     if ((rc = ensure_buf(&w.thr_g, &w.thr_bytes, (size_t)nq_pad * 4)) != ARCHI_OK) return rc;
     if ((rc = ensure_buf(&w.unverified, &w.unv_bytes, (size_t)(nq_pad + 1) * 4)) != ARCHI_OK) return rc;
-    if ((rc = ensure_buf(&w.cand, &w.cand_bytes, (size_t)grid * BM * cap * sizeof(uint2))) != ARCHI_OK) return rc;
-    if ((rc = ensure_buf(&w.cand_cnt, &w.cnt_bytes, (size_t)grid * BM * 4)) != ARCHI_OK) return rc;
+    if ((rc = ensure_buf(&w.cand, &w.cand_bytes, (size_t)grid * 2 * BM * cap * sizeof(uint2))) != ARCHI_OK) return rc;
+    if ((rc = ensure_buf(&w.cand_cnt, &w.cnt_bytes, (size_t)grid * 2 * BM * 4)) != ARCHI_OK) return rc;
     {
         void *before = w.aux;
         if ((rc = ensure_buf(&w.aux, &w.aux_bytes, (size_t)s->capacity * sizeof(float2))) != ARCHI_OK) return rc;
@@ -806,6 +821,10 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     cp.kprime = kprime;
     cp.cap = cap;
     cp.trigger = (cap - BN) < 2 * kprime ? (cap - BN) : 2 * kprime;
+    {
+        const char *dbg = getenv("ARCHI_TC_DEBUG");
+        cp.debug = dbg ? atoi(dbg) : 0;
+    }
     cp.exit_cap = exit_cap;
     cp.aux = reinterpret_cast<const float2 *>(w.aux);
     cp.cand = reinterpret_cast<uint2 *>(w.cand);
@@ -847,7 +866,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     sp.id_offset = id_offset;
     sp.unverified = w.unverified;
     sp.n_unverified = w.unverified + nq_pad;
-    const size_t sel_smem = (size_t)ngroups * exit_cap * 4;
+    const size_t sel_smem = (size_t)2 * ngroups * exit_cap * 4;
     ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sel_smem > 200 * 1024 ? 200 * 1024 : sel_smem)));
     ARCHI_REQUIRE(sel_smem <= 200 * 1024, "tensor path: select kernel needs %zu B of shared memory", sel_smem);
