@@ -534,14 +534,25 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     const int nlists = 2 * p.ngroups;
     auto list_base = [&](int l) { return ((size_t)((l >> 1) * p.qt_count + qt)) * 2 + (l & 1); };
 
-    if (tid == 0) {
-        int acc = 0;
-        for (int l = 0; l < nlists; ++l) {
-            s_off[l] = acc;
-            acc += p.cand_cnt[list_base(l) * BM + tq];
+    // list sizes -> exclusive offsets (parallel loads, one warp scans)
+    for (int l = tid; l < nlists; l += SEL_THREADS) s_off[l] = p.cand_cnt[list_base(l) * BM + tq];
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+        for (int b0 = 0; b0 < nlists; b0 += 32) {
+            const int v = (b0 + lane < nlists) ? s_off[b0 + lane] : 0;
+            int incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += o;
+            }
+            __syncwarp();
+            if (b0 + lane < nlists) s_off[b0 + lane] = carry + incl - v;
+            carry += __shfl_sync(kFull, incl, 31);
         }
-        s_off[nlists] = acc;
-        s_nk = 0;
+        if (lane == 0) s_off[nlists] = carry;
     }
     __syncthreads();
     const int total = s_off[nlists];
@@ -564,8 +575,10 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
             c = __reduce_add_sync(kFull, c);
             if (lane == 0 && c) atomicAdd(&s_count, c);
             __syncthreads();
-            if (s_count >= p.kprime) T = trial;
+            const int cnt_ge = s_count;
+            if (cnt_ge >= p.kprime) T = trial;
             __syncthreads();
+            if (cnt_ge == p.kprime) break;  // exactly kprime keys are >= T
         }
     }
     // gather the survivors (key >= T)
