@@ -243,15 +243,36 @@ def main():
             ms.append(st.last_kernel_ms)
         store.set_timing(False)
         launch_ms = float(np.median(ms))
-        nq_launch = min(q_dev.shape[0], 8) if st.path == N.PATH_STREAM else q_dev.shape[0]
-        algo_bytes = cnt * dim * elt + nq_launch * dim * 4 + nq_launch * k * 8
-        ach = algo_bytes / (launch_ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                "traffic": None, "peak_source": peaks["source"] + " hbm_gbs (copy, burst)",
-                "kernel": "scan_topk_kernel" if st.path == N.PATH_STREAM else "coarse_tc_kernel",
-                "launch_ms": launch_ms, "algorithmic_bytes_per_launch": algo_bytes,
-                "launches_per_step": st.passes, "grid": st.grid,
-                "frac_of_nominal_8TBps": ach / 8000.0}
+        nq_all = q_dev.shape[0]
+        if st.path == N.PATH_STREAM:
+            nq_launch = min(nq_all, 8)
+            algo_bytes = cnt * dim * elt + nq_launch * dim * 4 + nq_launch * k * 8
+            ach = algo_bytes / (launch_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                    "peak_source": peaks["source"] + " hbm_gbs (copy, burst)", "kernel": "scan_topk_kernel",
+                    "launch_ms": launch_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                    "launches_per_step": st.passes, "grid": st.grid, "frac_of_nominal_8TBps": ach / 8000.0}
+        # tensor-core path: one launch scores min(nq, 2048) queries against the whole shard
+        nq_launch = min(nq_all, 2048)
+        algo_bytes = cnt * dim * elt + nq_launch * dim * elt
+        algo_flops = 2.0 * nq_launch * cnt * dim
+        gbs = algo_bytes / (launch_ms * 1e-3) / 1e9
+        tfs = algo_flops / (launch_ms * 1e-3) / 1e12
+        t_hbm = algo_bytes / (peaks["hbm_gbs"] * 1e9)
+        t_tc = algo_flops / (peaks["bf16_tflops"] * 1e12)
+        common = {"traffic": None, "kernel": "tc_coarse_kernel<tf32>" if storage == "f32" else "tc_coarse_kernel<bf16>",
+                  "launch_ms": launch_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                  "algorithmic_flops_per_launch": algo_flops, "launches_per_step": st.passes, "grid": st.grid,
+                  "achieved_GBps": gbs, "achieved_TFLOPs": tfs, "frac_hbm": gbs / peaks["hbm_gbs"],
+                  "frac_tensor_bf16_peak": tfs / peaks["bf16_tflops"], "unverified_queries": st.unverified_queries}
+        if t_tc >= t_hbm:
+            note = " (kind::tf32 runs at half the bf16 rate; frac is against the bf16 peak)" if storage == "f32" else ""
+            return dict(common, bound="tensor", achieved=tfs, peak=peaks["bf16_tflops"], unit="TFLOP/s",
+                        frac=tfs / peaks["bf16_tflops"],
+                        peak_source=peaks["source"] + " bf16_tflops (cuBLAS 8192^3, burst)" + note)
+        return dict(common, bound="hbm", achieved=gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbs / peaks["hbm_gbs"],
+                    peak_source=peaks["source"] + " hbm_gbs (copy, burst)", frac_of_nominal_8TBps=gbs / 8000.0)
 
     def time_e2e(q_host, steps, warmup):
         """Public call with host buffers: pinned queries -> H2D -> search -> all-gather/merge -> D2H."""
