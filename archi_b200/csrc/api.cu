@@ -384,6 +384,7 @@ int archi_store_reset(archi_store_t *s)
     s->rows = 0;
     s->deleted = 0;
     s->epoch++;
+    s->reset_epoch++;
     return ARCHI_OK;
 }
 

@@ -77,6 +77,11 @@ struct TensorWorkspace {
     int *cand_cnt = nullptr;     size_t cnt_bytes = 0;
     void *aux = nullptr;         size_t aux_bytes = 0;      // [capacity] (a, b) per row
     float *max_norm2 = nullptr;
+    // bf16 shadow of an fp32 store: the coarse pass reads it (half the bytes, full-rate MMA); the
+    // exact rescoring still reads the fp32 rows
+    void *shadow = nullptr;      size_t shadow_bytes = 0;
+    int64_t shadow_rows = 0;     // rows [0, shadow_rows) are converted
+    int64_t shadow_reset_epoch = -1;
     int64_t maxnorm_epoch = -1;
     int64_t aux_epoch = -1;
     bool aux_alive = false, aux_had_filter = false;
@@ -102,6 +107,7 @@ struct archi_store {
     archi::Workspace ws;
     archi::TensorWorkspace tws;
     int64_t epoch = 0;        // bumped whenever rows / tombstones change (invalidates cached aux)
+    int64_t reset_epoch = 0;  // bumped when existing rows are discarded or moved (reset / load)
     std::mutex mu;
 };
 

@@ -77,6 +77,7 @@ struct PrepParams {
     uint32_t *thr_g;       // [nq] shared thresholds (mapped), reset to 0
     int *unverified;       // [nq]
     const float *max_norm2;// [1] max |row|^2 over the store
+    float corpus_rel_err;  // 2^-9 when the coarse pass reads a bf16 shadow of fp32 rows, else 0
 };
 
 __global__ void __launch_bounds__(128) tc_prep_kernel(const PrepParams p)
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(const PrepParams p)
         // tf32: both operands truncated to 10 mantissa bits -> 2^-9 (1 + 2^-11) |q|;
         // plus fp32 accumulation slack dim * 2^-22 |q|.
         float unit = p.tf32 ? 1.0005f * 0.001953125f * qn : sqrtf(e2) * 1.0001f;
+        unit += p.corpus_rel_err * 1.0005f * qn;   // |q~ . (c - bf16(c))| <= |q| 2^-9 |c|
         unit += (float)p.dim * 2.4e-7f * qn;
         const float maxn = sqrtf(*p.max_norm2);
         float eps;
@@ -157,6 +159,17 @@ __global__ void tc_aux_kernel(float2 *aux, const float *norm2, const uint32_t *a
     aux[i] = ab;
 }
 
+// fp32 rows -> bf16 shadow rows (row strides ld_src / ld_dst elements, padding zeroed)
+__global__ void tc_shadow_kernel(const float *src, __nv_bfloat16 *dst, long long first, long long n, int dim,
+                                 int ld_src, int ld_dst)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * ld_dst) return;
+    const long long r = first + i / ld_dst;
+    const int e = (int)(i % ld_dst);
+    dst[r * ld_dst + e] = __float2bfloat16_rn(e < dim ? src[r * ld_src + e] : 0.f);
+}
+
 __global__ void tc_maxnorm_kernel(const float *norm2, long long n, float *out)
 {
     float m = 0.f;
@@ -181,6 +194,8 @@ struct CoarseParams {
     int kprime;           // candidates kept per compaction
     int cap;              // entries per candidate buffer (C)
     int trigger;          // a buffer holding at least this many entries is compacted after the tile
+    int tile_begin, tile_end;  // corpus tiles [tile_begin, tile_end) are scanned by this launch
+    int resume;           // 1: continue from the candidate counts / thresholds left by a previous launch
     int debug;            // profiling aid (ARCHI_TC_DEBUG): 1 = skip the MMAs, 2 = skip the epilogue math
     int exit_cap;         // buffers larger than this are compacted before the CTA exits
     const float2 *aux;    // [n]
@@ -220,17 +235,36 @@ __device__ __forceinline__ void compact_buffer(uint2 *buf, int n, int kprime, in
             id[t] = e.y;
         }
     }
-    // bisection on the mapped key bits: largest T with count(uk >= T) >= kprime
-    uint32_t T = 0u;
-#pragma unroll 1
-    for (int b = 31; b >= 0; --b) {
-        const uint32_t trial = T | (1u << b);
-        int c = 0;
+    // Bisection on the mapped key bits for a T with kprime <= count(uk >= T) <= kprime + slack.
+    // Only the bits below the highest bit in which the largest and smallest key differ are searched.
+    uint32_t kmax = 0u, kmin = 0xffffffffu;
 #pragma unroll
-        for (int t = 0; t < SLOTS; ++t) c += (uk[t] >= trial) ? 1 : 0;
-        c = __reduce_add_sync(kFull, c);
-        if (c >= kprime) T = trial;
-        if (c == kprime) break;  // exactly kprime entries are >= T: T is already a valid threshold
+    for (int t = 0; t < SLOTS; ++t) {
+        if ((t * 32 + lane) < n) {
+            kmax = max(kmax, uk[t]);
+            kmin = min(kmin, uk[t]);
+        }
+    }
+    kmax = __reduce_max_sync(kFull, kmax);
+    kmin = __reduce_min_sync(kFull, kmin);
+    const uint32_t diff = kmax ^ kmin;
+    uint32_t T = kmin;                                   // all keys equal (or n <= kprime): keep everything
+    if (diff != 0u && n > kprime) {
+        const int hb = 31 - __clz(diff);
+        T = hb == 31 ? 0u : (kmax & ~((2u << hb) - 1u));  // common prefix of every key
+        const int slack = kprime >> 2;
+#pragma unroll 1
+        for (int b = hb; b >= 0; --b) {
+            const uint32_t trial = T | (1u << b);
+            int c = 0;
+#pragma unroll
+            for (int t = 0; t < SLOTS; ++t) c += (uk[t] >= trial) ? 1 : 0;
+            c = __reduce_add_sync(kFull, c);
+            if (c >= kprime) {
+                T = trial;
+                if (c <= kprime + slack) break;           // tight enough: stop early
+            }
+        }
     }
     // keep everything above T and only as many entries equal to T as are needed to reach kprime
     // (dropping a row whose coarse key equals the new threshold is covered by the proof)
@@ -238,7 +272,7 @@ __device__ __forceinline__ void compact_buffer(uint2 *buf, int n, int kprime, in
 #pragma unroll
     for (int t = 0; t < SLOTS; ++t) c_gt += (uk[t] > T) ? 1 : 0;
     c_gt = __reduce_add_sync(kFull, c_gt);
-    int need_eq = kprime - c_gt;
+    int need_eq = kprime - c_gt;                          // <= 0: no entry equal to T is needed
     int base = 0;
 #pragma unroll
     for (int t = 0; t < SLOTS; ++t) {
@@ -317,7 +351,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int ct = group; ct < p.n_ctiles; ct += p.ngroups) {
+            for (int ct = p.tile_begin + group; ct < p.tile_end; ct += p.ngroups) {
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
                     ptx::mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
@@ -340,7 +374,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                                    ((uint32_t)(BM >> 4) << 24);
             int s = 0, u = 0;
             uint32_t ph = 0;
-            for (int ct = group; ct < p.n_ctiles; ct += p.ngroups, ++u) {
+            for (int ct = p.tile_begin + group; ct < p.tile_end; ct += p.ngroups, ++u) {
                 const int acc = u & 1;
                 const uint32_t aph = (uint32_t)(u >> 1) & 1u;
                 ptx::mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);
@@ -385,9 +419,9 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         uint2 *buf = p.cand + (vcta * BM + tq) * p.cap;
         float2 *aux_w = s_aux + (warp - 2) * BN;         // this warp's private copy of the tile's (a, b)
         float thr = active ? -CUDART_INF_F : CUDART_INF_F;
-        int cnt = 0;
+        int cnt = (p.resume && active) ? p.cand_cnt[vcta * BM + tq] : 0;
         int u = grp;
-        for (int ct = group + grp * p.ngroups; ct < p.n_ctiles; ct += 2 * p.ngroups, u += 2) {
+        for (int ct = p.tile_begin + group + grp * p.ngroups; ct < p.tile_end; ct += 2 * p.ngroups, u += 2) {
             const uint32_t aph = (uint32_t)(u >> 1) & 1u;
             // this tile's per-row constants, fetched while the MMAs run (warp-private: no CTA barrier)
             __syncwarp();
@@ -404,27 +438,82 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BN);
             const uint32_t row_base = (uint32_t)ct * BN;
 
-            // one 32-column chunk, fully predicated (no branches, no slow path): a column whose key
-            // beats the threshold is stored at buf[cnt] by a predicated st.global and bumps cnt
+            // One 32-column chunk in two passes so that the loads / FMAs of all columns overlap:
+            //  (1) keys and a 32-bit admission mask (plain code, no ordering constraints);
+            //  (2) the few admitted columns are appended.  cnt <= cap - BN holds at every tile start
+            //      (compaction trigger), so a tile cannot overflow the buffer.
             auto process = [&](uint32_t (&r)[32], int c) {
+                uint32_t mask = 0u;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float2 ab = aux_w[c * 32 + j];
                     const float key = fmaf(__uint_as_float(r[j]), ab.x, ab.y);
-                    uint32_t took;
-                    asm volatile(
-                        "{\n\t"
-                        ".reg .pred p;\n\t"
-                        "setp.gt.f32 p, %2, %3;\n\t"
-                        "setp.lt.and.s32 p, %4, %5, p;\n\t"
-                        "@p st.global.v2.b32 [%1], {%6, %7};\n\t"
-                        "selp.u32 %0, 1, 0, p;\n\t"
-                        "}"
-                        : "=r"(took)
-                        : "l"(buf + cnt), "f"(key), "f"(thr), "r"(cnt), "r"(p.cap), "r"(__float_as_uint(key)),
-                          "r"(row_base + c * 32 + j)
-                        : "memory");
-                    cnt += (int)took;
+                    r[j] = __float_as_uint(key);
+                    mask |= (key > thr) ? (1u << j) : 0u;
+                }
+                // (2) columns admitted by ANY lane of the warp (few): visit them one by one; the column
+                //     index is warp-uniform, so picking the register is a uniform jump, and only the
+                //     lanes that admitted the column store (key, row id) into their own buffer
+                unsigned um = __reduce_or_sync(kFull, mask);
+                if (__popc(um) > 6) {
+                    // dense phase (loose thresholds): 32 predicated stores beat the column walk
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t bit = (mask >> j) & 1u;
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred p;\n\t"
+                            "setp.ne.u32 p, %3, 0;\n\t"
+                            "@p st.global.v2.b32 [%0], {%1, %2};\n\t"
+                            "}"
+                            :: "l"(buf + cnt), "r"(r[j]), "r"(row_base + c * 32 + j), "r"(bit));
+                        cnt += (int)bit;
+                    }
+                    um = 0u;
+                }
+                while (um) {
+                    const int j = __ffs(um) - 1;
+                    um &= um - 1;
+                    uint32_t kb;
+                    switch (j) {
+                        case 0: kb = r[0]; break;
+                        case 1: kb = r[1]; break;
+                        case 2: kb = r[2]; break;
+                        case 3: kb = r[3]; break;
+                        case 4: kb = r[4]; break;
+                        case 5: kb = r[5]; break;
+                        case 6: kb = r[6]; break;
+                        case 7: kb = r[7]; break;
+                        case 8: kb = r[8]; break;
+                        case 9: kb = r[9]; break;
+                        case 10: kb = r[10]; break;
+                        case 11: kb = r[11]; break;
+                        case 12: kb = r[12]; break;
+                        case 13: kb = r[13]; break;
+                        case 14: kb = r[14]; break;
+                        case 15: kb = r[15]; break;
+                        case 16: kb = r[16]; break;
+                        case 17: kb = r[17]; break;
+                        case 18: kb = r[18]; break;
+                        case 19: kb = r[19]; break;
+                        case 20: kb = r[20]; break;
+                        case 21: kb = r[21]; break;
+                        case 22: kb = r[22]; break;
+                        case 23: kb = r[23]; break;
+                        case 24: kb = r[24]; break;
+                        case 25: kb = r[25]; break;
+                        case 26: kb = r[26]; break;
+                        case 27: kb = r[27]; break;
+                        case 28: kb = r[28]; break;
+                        case 29: kb = r[29]; break;
+                        case 30: kb = r[30]; break;
+                        case 31: kb = r[31]; break;
+                        default: kb = 0u; break;
+                    }
+                    if ((mask >> j) & 1u) {
+                        buf[cnt] = make_uint2(kb, row_base + c * 32 + j);
+                        ++cnt;
+                    }
                 }
             };
             uint32_t ra[32], rb[32];
@@ -517,26 +606,39 @@ __device__ __forceinline__ float row_elem(const void *corpus, int dtype, size_t 
     return reinterpret_cast<const float *>(corpus)[idx];
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
-{
-    extern __shared__ uint32_t s_keys[];            // mapped coarse keys of every candidate of this query
-    __shared__ int s_off[320];                      // per-list offsets (2 * ngroups <= 296) + total
-    __shared__ int s_count;
-    __shared__ uint32_t s_T;
-    __shared__ int s_nk;
-    __shared__ uint32_t s_kid[KEPT_MAX];
-    __shared__ float s_kc[KEPT_MAX];                // coarse key of the kept candidates
-    __shared__ float s_ex[KEPT_MAX];                // exact key (coarse-key space)
-    __shared__ float s_sc[KEPT_MAX];                // output score
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int qt = q / BM, tq = q % BM;
-    // candidate lists of this query: one per (CTA of its query tile, epilogue group)
-    const int nlists = 2 * p.ngroups;
-    auto list_base = [&](int l) { return ((size_t)((l >> 1) * p.qt_count + qt)) * 2 + (l & 1); };
+// Shared front half of tc_select_kernel / tc_threshold_kernel (one CTA per query): stage the mapped
+// coarse keys of every candidate of query q in shared memory and find T, the kprime-th largest
+// (0 when there are at most kprime candidates).  Flat walk over (list, entry) with a binary search
+// on the list offsets, so every load of the walk is independent.
+struct SelCommon {
+    const uint2 *cand;
+    const int *cand_cnt;
+    int qt_count, ngroups, cap, kprime;
+};
 
-    // list sizes -> exclusive offsets (parallel loads, one warp scans)
-    for (int l = tid; l < nlists; l += SEL_THREADS) s_off[l] = p.cand_cnt[list_base(l) * BM + tq];
-    if (tid == 0) s_nk = 0;
+__device__ __forceinline__ size_t sel_list_base(const SelCommon &c, int l, int qt)
+{
+    return ((size_t)((l >> 1) * c.qt_count + qt)) * 2 + (l & 1);
+}
+
+__device__ __forceinline__ int sel_locate(const int *s_off, int nlists, int f)
+{
+    int lo = 0, hi = nlists;              // largest g with s_off[g] <= f
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= f) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t sel_stage_and_bisect(const SelCommon &c, int q, uint32_t *s_keys, int *s_off,
+                                                        int *s_count, int &total_out)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qt = q / BM, tq = q % BM;
+    const int nlists = 2 * c.ngroups;
+    for (int l = tid; l < nlists; l += SEL_THREADS) s_off[l] = c.cand_cnt[sel_list_base(c, l, qt) * BM + tq];
     __syncthreads();
     if (warp == 0) {
         int carry = 0;
@@ -556,43 +658,86 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     }
     __syncthreads();
     const int total = s_off[nlists];
-    for (int g = 0; g < nlists; ++g) {
-        const int n_g = s_off[g + 1] - s_off[g];
-        const uint2 *src = p.cand + (list_base(g) * BM + tq) * p.cap;
-        for (int i = tid; i < n_g; i += SEL_THREADS) s_keys[s_off[g] + i] = fmap(__uint_as_float(src[i].x));
+    total_out = total;
+#pragma unroll 4
+    for (int f = tid; f < total; f += SEL_THREADS) {
+        const int g = sel_locate(s_off, nlists, f);
+        const uint2 *src = c.cand + (sel_list_base(c, g, qt) * BM + tq) * c.cap;
+        s_keys[f] = fmap(__uint_as_float(src[f - s_off[g]].x));
     }
     __syncthreads();
-
-    // T = kprime-th largest mapped key (0 when there are at most kprime candidates)
     uint32_t T = 0u;
-    if (total > p.kprime) {
+    if (total > c.kprime) {
         for (int b = 31; b >= 0; --b) {
             const uint32_t trial = T | (1u << b);
-            if (tid == 0) s_count = 0;
+            if (tid == 0) *s_count = 0;
             __syncthreads();
-            int c = 0;
-            for (int i = tid; i < total; i += SEL_THREADS) c += (s_keys[i] >= trial) ? 1 : 0;
-            c = __reduce_add_sync(kFull, c);
-            if (lane == 0 && c) atomicAdd(&s_count, c);
+            int n = 0;
+            for (int i = tid; i < total; i += SEL_THREADS) n += (s_keys[i] >= trial) ? 1 : 0;
+            n = __reduce_add_sync(kFull, n);
+            if (lane == 0 && n) atomicAdd(s_count, n);
             __syncthreads();
-            const int cnt_ge = s_count;
-            if (cnt_ge >= p.kprime) T = trial;
+            const int cnt_ge = *s_count;
+            if (cnt_ge >= c.kprime) T = trial;
             __syncthreads();
-            if (cnt_ge == p.kprime) break;  // exactly kprime keys are >= T
+            if (cnt_ge == c.kprime) break;  // exactly kprime keys are >= T
         }
     }
+    return T;
+}
+
+// After the warm-up phase: publish, per query, the kprime-th best coarse key over ALL its candidate
+// lists as the shared threshold.  It is a valid lower bound of the final kprime-th best (the rows seen
+// so far are a subset of the corpus) and far tighter than any single CTA's local threshold.
+struct ThresholdParams {
+    SelCommon c;
+    uint32_t *thr_g;
+};
+
+__global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const ThresholdParams p)
+{
+    extern __shared__ uint32_t s_keys[];
+    __shared__ int s_off[320];
+    __shared__ int s_count;
+    int total;
+    const uint32_t T = sel_stage_and_bisect(p.c, blockIdx.x, s_keys, s_off, &s_count, total);
+    if (threadIdx.x == 0 && total > p.c.kprime) atomicMax(p.thr_g + blockIdx.x, T);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
+{
+    extern __shared__ uint32_t s_keys[];            // mapped coarse keys of every candidate of this query
+    __shared__ int s_off[320];                      // per-list offsets (2 * ngroups <= 296) + total
+    __shared__ int s_count;
+    __shared__ int s_nk;
+    __shared__ uint32_t s_kid[KEPT_MAX];
+    __shared__ float s_kc[KEPT_MAX];                // coarse key of the kept candidates
+    __shared__ float s_ex[KEPT_MAX];                // exact key (coarse-key space)
+    __shared__ float s_sc[KEPT_MAX];                // output score
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qt = q / BM, tq = q % BM;
+    const int nlists = 2 * p.ngroups;
+    SelCommon sc;
+    sc.cand = p.cand;
+    sc.cand_cnt = p.cand_cnt;
+    sc.qt_count = p.qt_count;
+    sc.ngroups = p.ngroups;
+    sc.cap = p.cap;
+    sc.kprime = p.kprime;
+    if (tid == 0) s_nk = 0;
+    int total;
+    const uint32_t T = sel_stage_and_bisect(sc, q, s_keys, s_off, &s_count, total);
+
     // gather the survivors (key >= T)
-    for (int g = 0; g < nlists; ++g) {
-        const int n_g = s_off[g + 1] - s_off[g];
-        const uint2 *src = p.cand + (list_base(g) * BM + tq) * p.cap;
-        for (int i = tid; i < n_g; i += SEL_THREADS) {
-            if (s_keys[s_off[g] + i] >= T) {
-                const int slot = atomicAdd(&s_nk, 1);
-                if (slot < KEPT_MAX) {
-                    const uint2 e = src[i];
-                    s_kid[slot] = e.y;
-                    s_kc[slot] = __uint_as_float(e.x);
-                }
+#pragma unroll 4
+    for (int f = tid; f < total; f += SEL_THREADS) {
+        if (s_keys[f] >= T) {
+            const int g = sel_locate(s_off, nlists, f);
+            const uint2 e = p.cand[(sel_list_base(sc, g, qt) * BM + tq) * p.cap + (f - s_off[g])];
+            const int slot = atomicAdd(&s_nk, 1);
+            if (slot < KEPT_MAX) {
+                s_kid[slot] = e.y;
+                s_kc[slot] = __uint_as_float(e.x);
             }
         }
     }
@@ -741,9 +886,14 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
 {
     using namespace tc;
     TensorWorkspace &w = s->tws;
-    const bool tf32 = s->dtype == ARCHI_F32;
+    // fp32 stores: the coarse pass reads a bf16 shadow copy (ARCHI_NO_SHADOW=1 keeps kind::tf32 on the
+    // fp32 rows instead: no extra memory, half the MMA rate and twice the bytes)
+    static const bool no_shadow = getenv("ARCHI_NO_SHADOW") && atoi(getenv("ARCHI_NO_SHADOW")) != 0;
+    const bool use_shadow = s->dtype == ARCHI_F32 && !no_shadow;
+    const bool tf32 = s->dtype == ARCHI_F32 && !use_shadow;
     const int kelems = tf32 ? 32 : 64;
     const int ldq = round_up(s->dim, tf32 ? 4 : 8);
+    const int ld_sh = round_up(s->dim, 8);
     const int qt_count = (nq + BM - 1) / BM;
     ARCHI_REQUIRE(qt_count <= MAX_QT, "tensor path: at most %d queries per launch", MAX_QT * BM);
     const int nq_pad = qt_count * BM;
@@ -774,11 +924,27 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     if ((rc = ensure_buf(&w.cand, &w.cand_bytes, (size_t)grid * 2 * BM * cap * sizeof(uint2))) != ARCHI_OK) return rc;
     if ((rc = ensure_buf(&w.cand_cnt, &w.cnt_bytes, (size_t)grid * 2 * BM * 4)) != ARCHI_OK) return rc;
     {
-        void *before = w.aux;
-        if ((rc = ensure_buf(&w.aux, &w.aux_bytes, (size_t)s->capacity * sizeof(float2))) != ARCHI_OK) return rc;
-        if (w.aux != before) w.aux_epoch = -1;
+        const size_t need = (size_t)s->capacity * sizeof(float2);
+        const bool realloc = !w.aux || w.aux_bytes < need;
+        if ((rc = ensure_buf(&w.aux, &w.aux_bytes, need)) != ARCHI_OK) return rc;
+        if (realloc) w.aux_epoch = -1;
     }
     if (!w.max_norm2) ARCHI_CUDA(cudaMalloc(&w.max_norm2, 4));
+    if (use_shadow) {
+        const size_t need = (size_t)s->capacity * ld_sh * 2;
+        const bool realloc = !w.shadow || w.shadow_bytes < need;
+        if ((rc = ensure_buf(&w.shadow, &w.shadow_bytes, need)) != ARCHI_OK) return rc;
+        if (realloc || w.shadow_reset_epoch != s->reset_epoch) w.shadow_rows = 0;
+        w.shadow_reset_epoch = s->reset_epoch;
+        if (w.shadow_rows < s->rows) {
+            const long long n_new = s->rows - w.shadow_rows;
+            const long long tot = n_new * ld_sh;
+            tc_shadow_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+                (const float *)s->data, (__nv_bfloat16 *)w.shadow, w.shadow_rows, n_new, s->dim, s->ld, ld_sh);
+            ARCHI_CHECK_LAUNCH();
+            w.shadow_rows = s->rows;
+        }
+    }
 
     // ---- cached per-store data: max |row|^2 and the (a, b) constants ----
     if (w.maxnorm_epoch != s->epoch) {
@@ -815,6 +981,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     pp.thr_g = w.thr_g;
     pp.unverified = w.unverified;
     pp.max_norm2 = w.max_norm2;
+    pp.corpus_rel_err = use_shadow ? 0.001953125f : 0.f;
     ARCHI_CUDA(cudaMemsetAsync(w.unverified + nq_pad, 0, 4, st));
     tc_prep_kernel<<<nq, 128, 0, st>>>(pp);
     ARCHI_CHECK_LAUNCH();
@@ -822,18 +989,19 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     // ---- 3. coarse scorer ----
     CUtensorMap tmap_q, tmap_c;
     if ((rc = make_tmap(&tmap_q, w.qstage, tf32, nq_pad, ldq, BM)) != ARCHI_OK) return rc;
-    if ((rc = make_tmap(&tmap_c, s->data, tf32, s->rows, s->ld, BN)) != ARCHI_OK) return rc;
+    if ((rc = make_tmap(&tmap_c, use_shadow ? w.shadow : s->data, tf32, s->rows, use_shadow ? ld_sh : s->ld, BN)) != ARCHI_OK)
+        return rc;
     CoarseParams cp;
     cp.n = s->rows;
     cp.n_ctiles = n_ctiles;
-    cp.kchunks = (s->ld + kelems - 1) / kelems;
+    cp.kchunks = ((use_shadow ? ld_sh : s->ld) + kelems - 1) / kelems;
     cp.kelems = kelems;
     cp.nq = nq;
     cp.qt_count = qt_count;
     cp.ngroups = ngroups;
     cp.kprime = kprime;
     cp.cap = cap;
-    cp.trigger = (cap - BN) < 2 * kprime ? (cap - BN) : 2 * kprime;
+    cp.trigger = cap - BN;   // lazy: appends are cheap (predicated stores), compactions are not
     {
         const char *dbg = getenv("ARCHI_TC_DEBUG");
         cp.debug = dbg ? atoi(dbg) : 0;
@@ -845,7 +1013,45 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     cp.thr_g = w.thr_g;
     auto kern = tf32 ? tc_coarse_kernel<true> : tc_coarse_kernel<false>;
     ARCHI_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const size_t sel_smem = (size_t)2 * ngroups * exit_cap * 4;
+    ARCHI_REQUIRE(sel_smem <= 200 * 1024, "tensor path: select kernel needs %zu B of shared memory", sel_smem);
+    ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+
+    // Warm-up phase: scan the first ~1/16 of the corpus tiles, then turn the candidates of ALL CTAs
+    // into one shared threshold per query (tc_threshold_kernel) before scanning the rest.  The
+    // thresholds of the main phase are then ~ngroups times tighter than any CTA-local one, and its
+    // epilogue almost never stores a candidate.
+    static const int warm_div = getenv("ARCHI_TC_WARM_DIV") ? atoi(getenv("ARCHI_TC_WARM_DIV")) : 16;
+    int warm_tiles = 0;
+    if (warm_div > 1 && n_ctiles >= 24 * ngroups) {
+        warm_tiles = round_up(n_ctiles / warm_div, 2 * ngroups);   // every epilogue group gets whole tiles
+        if (warm_tiles < 4 * ngroups) warm_tiles = 4 * ngroups;
+    }
     if (s->timing) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
+    if (warm_tiles > 0) {
+        cp.tile_begin = 0;
+        cp.tile_end = warm_tiles;
+        cp.resume = 0;
+        const int keep_exit = cp.exit_cap;
+        if (cp.exit_cap > cp.trigger - 1) cp.exit_cap = cp.trigger - 1;   // resumable: room for a whole tile
+        kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmap_q, tmap_c, cp);
+        ARCHI_CHECK_LAUNCH();
+        cp.exit_cap = keep_exit;
+        ThresholdParams tp;
+        tp.c.cand = reinterpret_cast<const uint2 *>(w.cand);
+        tp.c.cand_cnt = w.cand_cnt;
+        tp.c.qt_count = qt_count;
+        tp.c.ngroups = ngroups;
+        tp.c.cap = cap;
+        tp.c.kprime = kprime;
+        tp.thr_g = w.thr_g;
+        tc_threshold_kernel<<<nq, SEL_THREADS, sel_smem, st>>>(tp);
+        ARCHI_CHECK_LAUNCH();
+    }
+    cp.tile_begin = warm_tiles;
+    cp.tile_end = n_ctiles;
+    cp.resume = warm_tiles > 0 ? 1 : 0;
     kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmap_q, tmap_c, cp);
     ARCHI_CHECK_LAUNCH();
     if (s->timing) {
@@ -879,10 +1085,6 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     sp.id_offset = id_offset;
     sp.unverified = w.unverified;
     sp.n_unverified = w.unverified + nq_pad;
-    const size_t sel_smem = (size_t)2 * ngroups * exit_cap * 4;
-    ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(sel_smem > 200 * 1024 ? 200 * 1024 : sel_smem)));
-    ARCHI_REQUIRE(sel_smem <= 200 * 1024, "tensor path: select kernel needs %zu B of shared memory", sel_smem);
     tc_select_kernel<<<nq, SEL_THREADS, sel_smem, st>>>(sp);
     ARCHI_CHECK_LAUNCH();
 
@@ -897,7 +1099,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
 
 void free_tensor_workspace(TensorWorkspace &w)
 {
-    void *ptrs[] = {w.qstage, w.qinfo, w.thr_g, w.unverified, w.cand, w.cand_cnt, w.aux, w.max_norm2};
+    void *ptrs[] = {w.qstage, w.qinfo, w.thr_g, w.unverified, w.cand, w.cand_cnt, w.aux, w.max_norm2, w.shadow};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     w = TensorWorkspace();
