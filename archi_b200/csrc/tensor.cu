@@ -420,6 +420,21 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         float2 *aux_w = s_aux + (warp - 2) * BN;         // this warp's private copy of the tile's (a, b)
         float thr = active ? -CUDART_INF_F : CUDART_INF_F;
         int cnt = (p.resume && active) ? p.cand_cnt[vcta * BM + tq] : 0;
+        if (p.resume && active) {
+            // a resumed launch starts from the shared threshold published by tc_threshold_kernel:
+            // drop (lane-parallel, no selection needed) everything the new threshold already excludes
+            thr = thr_from_word(__ldcg(p.thr_g + q));
+            int w = 0;
+            for (int i0 = 0; i0 < cnt; i0 += 8) {
+                uint2 e[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) e[j] = i0 + j < cnt ? buf[i0 + j] : make_uint2(0xff800000u, 0u);  // -inf
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (i0 + j < cnt && __uint_as_float(e[j].x) >= thr) buf[w++] = e[j];
+            }
+            cnt = w;
+        }
         int u = grp;
         for (int ct = p.tile_begin + group + grp * p.ngroups; ct < p.tile_end; ct += 2 * p.ngroups, u += 2) {
             const uint32_t aph = (uint32_t)(u >> 1) & 1u;
@@ -606,10 +621,11 @@ __device__ __forceinline__ float row_elem(const void *corpus, int dtype, size_t 
     return reinterpret_cast<const float *>(corpus)[idx];
 }
 
-// Shared front half of tc_select_kernel / tc_threshold_kernel (one CTA per query): stage the mapped
-// coarse keys of every candidate of query q in shared memory and find T, the kprime-th largest
-// (0 when there are at most kprime candidates).  Flat walk over (list, entry) with a binary search
-// on the list offsets, so every load of the walk is independent.
+// Shared front half of tc_select_kernel / tc_threshold_kernel (one CTA per query): T = the
+// kprime-th largest mapped coarse key over every candidate list of query q (0 when there are at most
+// kprime candidates).  MSB-first radix select, 8 bits per pass: each pass re-walks the lists in
+// global memory (L2-resident, coalesced: warp w takes lists w, w+8, ...; lanes take entries), builds
+// a 256-bin histogram of the keys that match the prefix found so far, and one warp picks the digit.
 struct SelCommon {
     const uint2 *cand;
     const int *cand_cnt;
@@ -621,72 +637,110 @@ __device__ __forceinline__ size_t sel_list_base(const SelCommon &c, int l, int q
     return ((size_t)((l >> 1) * c.qt_count + qt)) * 2 + (l & 1);
 }
 
-__device__ __forceinline__ int sel_locate(const int *s_off, int nlists, int f)
-{
-    int lo = 0, hi = nlists;              // largest g with s_off[g] <= f
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_off[mid] <= f) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
+constexpr int SEL_STAGE = 10240;   // keys staged in shared memory for the radix passes when they fit
 
-__device__ __forceinline__ uint32_t sel_stage_and_bisect(const SelCommon &c, int q, uint32_t *s_keys, int *s_off,
-                                                        int *s_count, int &total_out)
+// s_cnt[320], s_hist[256], s_misc[4], s_stage[SEL_STAGE] are shared-memory scratch; returns T, total via total_out
+__device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int q, int *s_cnt, int *s_hist, int *s_misc,
+                                                       uint32_t *s_stage, int &total_out)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qt = q / BM, tq = q % BM;
     const int nlists = 2 * c.ngroups;
-    for (int l = tid; l < nlists; l += SEL_THREADS) s_off[l] = c.cand_cnt[sel_list_base(c, l, qt) * BM + tq];
+    if (tid == 0) s_misc[0] = 0;
     __syncthreads();
-    if (warp == 0) {
-        int carry = 0;
-        for (int b0 = 0; b0 < nlists; b0 += 32) {
-            const int v = (b0 + lane < nlists) ? s_off[b0 + lane] : 0;
-            int incl = v;
+    int part = 0;
+    for (int l = tid; l < nlists; l += SEL_THREADS) {
+        const int n = c.cand_cnt[sel_list_base(c, l, qt) * BM + tq];
+        s_cnt[l] = n;
+        part += n;
+    }
+    part = __reduce_add_sync(kFull, part);
+    if (lane == 0 && part) atomicAdd(&s_misc[0], part);
+    __syncthreads();
+    const int total = s_misc[0];
+    total_out = total;
+    if (total <= c.kprime) return 0u;
+    const bool staged = total <= SEL_STAGE;
+    if (staged) {
+        // one walk over global memory; slots are claimed per list chunk (order is irrelevant)
+        if (tid == 0) s_misc[3] = 0;
+        __syncthreads();
+        for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
+            const int n = s_cnt[l];
+            const uint2 *src = c.cand + (sel_list_base(c, l, qt) * BM + tq) * c.cap;
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int m = n - i0 < 32 ? n - i0 : 32;
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(&s_misc[3], m);
+                slot = __shfl_sync(kFull, slot, 0);
+                if (lane < m) s_stage[slot + lane] = fmap(__uint_as_float(src[i0 + lane].x));
+            }
+        }
+        __syncthreads();
+    }
+
+    uint32_t prefix = 0u, known = 0u;   // bits of T fixed so far / their mask
+    int need = c.kprime;                // rank still to be located inside the current prefix bucket
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 256; i += SEL_THREADS) s_hist[i] = 0;
+        __syncthreads();
+        if (staged) {
+            for (int i = tid; i < total; i += SEL_THREADS) {
+                const uint32_t key = s_stage[i];
+                if ((key & known) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+            }
+        } else {
+            for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
+                const int n = s_cnt[l];
+                const uint2 *src = c.cand + (sel_list_base(c, l, qt) * BM + tq) * c.cap;
+                for (int i = lane; i < n; i += 32) {
+                    const uint32_t key = fmap(__uint_as_float(src[i].x));
+                    if ((key & known) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+                }
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane L owns bins [8L, 8L+8); walk from the top bin down until `need` keys are covered
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mine += s_hist[lane * 8 + j];
+            // inclusive suffix sum over lanes (bins of higher lanes hold larger keys)
+            int suf = mine;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(kFull, incl, d);
-                if (lane >= d) incl += o;
+                const int o = __shfl_down_sync(kFull, suf, d);
+                if (lane + d < 32) suf += o;
             }
-            __syncwarp();
-            if (b0 + lane < nlists) s_off[b0 + lane] = carry + incl - v;
-            carry += __shfl_sync(kFull, incl, 31);
+            const int above = suf - mine;           // keys in bins owned by higher lanes
+            const bool here = above < need && suf >= need;     // the crossing happens in my 8 bins
+            const unsigned who = __ballot_sync(kFull, here);
+            const int src_lane = __ffs(who) - 1;
+            if (lane == src_lane) {
+                int acc = above, digit = lane * 8;
+                for (int j = 7; j >= 0; --j) {
+                    const int h = s_hist[lane * 8 + j];
+                    if (acc + h >= need) {
+                        digit = lane * 8 + j;
+                        break;
+                    }
+                    acc += h;
+                }
+                s_misc[1] = digit;
+                s_misc[2] = need - acc;                         // rank inside the chosen bin
+            }
         }
-        if (lane == 0) s_off[nlists] = carry;
+        __syncthreads();
+        prefix |= (uint32_t)s_misc[1] << shift;
+        known |= 255u << shift;
+        need = s_misc[2];
+        __syncthreads();
     }
-    __syncthreads();
-    const int total = s_off[nlists];
-    total_out = total;
-#pragma unroll 4
-    for (int f = tid; f < total; f += SEL_THREADS) {
-        const int g = sel_locate(s_off, nlists, f);
-        const uint2 *src = c.cand + (sel_list_base(c, g, qt) * BM + tq) * c.cap;
-        s_keys[f] = fmap(__uint_as_float(src[f - s_off[g]].x));
-    }
-    __syncthreads();
-    uint32_t T = 0u;
-    if (total > c.kprime) {
-        for (int b = 31; b >= 0; --b) {
-            const uint32_t trial = T | (1u << b);
-            if (tid == 0) *s_count = 0;
-            __syncthreads();
-            int n = 0;
-            for (int i = tid; i < total; i += SEL_THREADS) n += (s_keys[i] >= trial) ? 1 : 0;
-            n = __reduce_add_sync(kFull, n);
-            if (lane == 0 && n) atomicAdd(s_count, n);
-            __syncthreads();
-            const int cnt_ge = *s_count;
-            if (cnt_ge >= c.kprime) T = trial;
-            __syncthreads();
-            if (cnt_ge == c.kprime) break;  // exactly kprime keys are >= T
-        }
-    }
-    return T;
+    return prefix;
 }
 
-// After the warm-up phase: publish, per query, the kprime-th best coarse key over ALL its candidate
+// After a warm-up phase: publish, per query, the kprime-th best coarse key over ALL its candidate
 // lists as the shared threshold.  It is a valid lower bound of the final kprime-th best (the rows seen
 // so far are a subset of the corpus) and far tighter than any single CTA's local threshold.
 struct ThresholdParams {
@@ -696,19 +750,21 @@ struct ThresholdParams {
 
 __global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const ThresholdParams p)
 {
-    extern __shared__ uint32_t s_keys[];
-    __shared__ int s_off[320];
-    __shared__ int s_count;
+    __shared__ int s_cnt[320];
+    __shared__ int s_hist[256];
+    __shared__ int s_misc[4];
+    __shared__ uint32_t s_stage[SEL_STAGE];
     int total;
-    const uint32_t T = sel_stage_and_bisect(p.c, blockIdx.x, s_keys, s_off, &s_count, total);
+    const uint32_t T = sel_radix_threshold(p.c, blockIdx.x, s_cnt, s_hist, s_misc, s_stage, total);
     if (threadIdx.x == 0 && total > p.c.kprime) atomicMax(p.thr_g + blockIdx.x, T);
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
 {
-    extern __shared__ uint32_t s_keys[];            // mapped coarse keys of every candidate of this query
-    __shared__ int s_off[320];                      // per-list offsets (2 * ngroups <= 296) + total
-    __shared__ int s_count;
+    __shared__ int s_cnt[320];                      // per-list sizes (2 * ngroups <= 296)
+    __shared__ int s_hist[256];
+    __shared__ int s_misc[4];
+    __shared__ uint32_t s_stage[SEL_STAGE];
     __shared__ int s_nk;
     __shared__ uint32_t s_kid[KEPT_MAX];
     __shared__ float s_kc[KEPT_MAX];                // coarse key of the kept candidates
@@ -726,18 +782,21 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     sc.kprime = p.kprime;
     if (tid == 0) s_nk = 0;
     int total;
-    const uint32_t T = sel_stage_and_bisect(sc, q, s_keys, s_off, &s_count, total);
+    const uint32_t T = sel_radix_threshold(sc, q, s_cnt, s_hist, s_misc, s_stage, total);
+    __syncthreads();
 
     // gather the survivors (key >= T)
-#pragma unroll 4
-    for (int f = tid; f < total; f += SEL_THREADS) {
-        if (s_keys[f] >= T) {
-            const int g = sel_locate(s_off, nlists, f);
-            const uint2 e = p.cand[(sel_list_base(sc, g, qt) * BM + tq) * p.cap + (f - s_off[g])];
-            const int slot = atomicAdd(&s_nk, 1);
-            if (slot < KEPT_MAX) {
-                s_kid[slot] = e.y;
-                s_kc[slot] = __uint_as_float(e.x);
+    for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
+        const int n = s_cnt[l];
+        const uint2 *src = p.cand + (sel_list_base(sc, l, qt) * BM + tq) * p.cap;
+        for (int i = lane; i < n; i += 32) {
+            const uint2 e = src[i];
+            if (fmap(__uint_as_float(e.x)) >= T) {
+                const int slot = atomicAdd(&s_nk, 1);
+                if (slot < KEPT_MAX) {
+                    s_kid[slot] = e.y;
+                    s_kc[slot] = __uint_as_float(e.x);
+                }
             }
         }
     }
@@ -901,19 +960,13 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     if (kprime > 256) kprime = 256;
     // buffer capacity: after a compaction (kprime entries) a buffer absorbs cap - BN - kprime more
     // candidates before the next one; a whole tile (BN) always fits
-    const int cap = kprime <= 128 ? 512 : 1024;
+    const int cap = 1024;
     const int n_ctiles = (int)((s->rows + BN - 1) / BN);
     int ngroups = s->sm_count / qt_count;
     if (ngroups > 148) ngroups = 148;
     if (ngroups < 1) ngroups = 1;
     if (ngroups > n_ctiles) ngroups = n_ctiles;
-    // the select kernel keeps every surviving candidate key of one query in shared memory
-    // (2 lists per CTA of the query's tile, at least kprime entries each)
-    if (2 * ngroups * kprime > 49152) ngroups = 49152 / (2 * kprime);
     const int grid = ngroups * qt_count;
-    int exit_cap = 49152 / (2 * ngroups);
-    if (exit_cap < kprime) exit_cap = kprime;
-    if (exit_cap > cap) exit_cap = cap;
 
     // ---- workspace ----
     int rc;
@@ -1001,59 +1054,54 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     cp.ngroups = ngroups;
     cp.kprime = kprime;
     cp.cap = cap;
-    cp.trigger = cap - BN;   // lazy: appends are cheap (predicated stores), compactions are not
+    cp.trigger = cap - BN + 1;   // lazy: appends are cheap, compactions are not; a whole tile always fits
     {
         const char *dbg = getenv("ARCHI_TC_DEBUG");
         cp.debug = dbg ? atoi(dbg) : 0;
     }
-    cp.exit_cap = exit_cap;
+    cp.exit_cap = cap;           // final launch: nothing to bound (the select kernel walks global memory)
     cp.aux = reinterpret_cast<const float2 *>(w.aux);
     cp.cand = reinterpret_cast<uint2 *>(w.cand);
     cp.cand_cnt = w.cand_cnt;
     cp.thr_g = w.thr_g;
     auto kern = tf32 ? tc_coarse_kernel<true> : tc_coarse_kernel<false>;
     ARCHI_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    const size_t sel_smem = (size_t)2 * ngroups * exit_cap * 4;
-    ARCHI_REQUIRE(sel_smem <= 200 * 1024, "tensor path: select kernel needs %zu B of shared memory", sel_smem);
-    ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-    ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-
-    // Warm-up phase: scan the first ~1/16 of the corpus tiles, then turn the candidates of ALL CTAs
-    // into one shared threshold per query (tc_threshold_kernel) before scanning the rest.  The
-    // thresholds of the main phase are then ~ngroups times tighter than any CTA-local one, and its
-    // epilogue almost never stores a candidate.
-    static const int warm_div = getenv("ARCHI_TC_WARM_DIV") ? atoi(getenv("ARCHI_TC_WARM_DIV")) : 16;
-    int warm_tiles = 0;
-    if (warm_div > 1 && n_ctiles >= 24 * ngroups) {
-        warm_tiles = round_up(n_ctiles / warm_div, 2 * ngroups);   // every epilogue group gets whole tiles
-        if (warm_tiles < 4 * ngroups) warm_tiles = 4 * ngroups;
+    // Warm-up phases.  Thresholds local to one (CTA, epilogue group) only ever see 1/(2*ngroups) of
+    // the rows, so most of a plain run is spent storing candidates that a global view would reject.
+    // Instead: (1) every epilogue group scans ONE tile and keeps everything; tc_threshold_kernel turns
+    // the union of all lists into one shared threshold per query (the kprime-th best of those rows --
+    // a valid lower bound of the final one); (2) the same after ~1/16 of the corpus; (3) the rest of
+    // the corpus then runs with thresholds ~2*ngroups times tighter than local ones and its epilogue
+    // almost never stores.  ARCHI_TC_WARM=0 disables the scheme.
+    static const int warm = getenv("ARCHI_TC_WARM") ? atoi(getenv("ARCHI_TC_WARM")) : 1;
+    int bounds[4] = {0, 0, 0, 0};
+    int n_phases = 1;
+    if (warm && n_ctiles >= 8 * ngroups) {
+        bounds[n_phases++] = 2 * ngroups < 40 ? 2 * ngroups : 40;   // <= 40 x 256 keys per query: staged select
+        if (n_ctiles >= 48 * ngroups) bounds[n_phases++] = round_up(n_ctiles / 16, 2 * ngroups);
     }
+    bounds[n_phases] = n_ctiles;
+    ThresholdParams tp;
+    tp.c.cand = reinterpret_cast<const uint2 *>(w.cand);
+    tp.c.cand_cnt = w.cand_cnt;
+    tp.c.qt_count = qt_count;
+    tp.c.ngroups = ngroups;
+    tp.c.cap = cap;
+    tp.c.kprime = kprime;
+    tp.thr_g = w.thr_g;
     if (s->timing) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
-    if (warm_tiles > 0) {
-        cp.tile_begin = 0;
-        cp.tile_end = warm_tiles;
-        cp.resume = 0;
-        const int keep_exit = cp.exit_cap;
-        if (cp.exit_cap > cp.trigger - 1) cp.exit_cap = cp.trigger - 1;   // resumable: room for a whole tile
+    for (int ph = 0; ph < n_phases; ++ph) {
+        cp.tile_begin = bounds[ph];
+        cp.tile_end = bounds[ph + 1];
+        cp.resume = ph > 0;
+        cp.exit_cap = ph + 1 < n_phases ? cap - BN : cap;   // resumable launches leave room for a whole tile
         kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmap_q, tmap_c, cp);
         ARCHI_CHECK_LAUNCH();
-        cp.exit_cap = keep_exit;
-        ThresholdParams tp;
-        tp.c.cand = reinterpret_cast<const uint2 *>(w.cand);
-        tp.c.cand_cnt = w.cand_cnt;
-        tp.c.qt_count = qt_count;
-        tp.c.ngroups = ngroups;
-        tp.c.cap = cap;
-        tp.c.kprime = kprime;
-        tp.thr_g = w.thr_g;
-        tc_threshold_kernel<<<nq, SEL_THREADS, sel_smem, st>>>(tp);
-        ARCHI_CHECK_LAUNCH();
+        if (ph + 1 < n_phases) {
+            tc_threshold_kernel<<<nq, SEL_THREADS, 0, st>>>(tp);
+            ARCHI_CHECK_LAUNCH();
+        }
     }
-    cp.tile_begin = warm_tiles;
-    cp.tile_end = n_ctiles;
-    cp.resume = warm_tiles > 0 ? 1 : 0;
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmap_q, tmap_c, cp);
-    ARCHI_CHECK_LAUNCH();
     if (s->timing) {
         ARCHI_CUDA(cudaEventRecord(s->ws.ev1, st));
         ARCHI_CUDA(cudaEventSynchronize(s->ws.ev1));
@@ -1085,7 +1133,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     sp.id_offset = id_offset;
     sp.unverified = w.unverified;
     sp.n_unverified = w.unverified + nq_pad;
-    tc_select_kernel<<<nq, SEL_THREADS, sel_smem, st>>>(sp);
+    tc_select_kernel<<<nq, SEL_THREADS, 0, st>>>(sp);
     ARCHI_CHECK_LAUNCH();
 
     // ---- the proof's verdict (4 bytes + flags) ----
