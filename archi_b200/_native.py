@@ -32,7 +32,8 @@ EXPORTS = [
 
 class SearchStats(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int), ("passes", ctypes.c_int), ("grid", ctypes.c_int),
-                ("unverified_queries", ctypes.c_int), ("last_kernel_ms", ctypes.c_double)]
+                ("unverified_queries", ctypes.c_int), ("last_kernel_ms", ctypes.c_double),
+                ("coarse_dtype", ctypes.c_int), ("coarse_launches", ctypes.c_int)]
 
 
 class NativeError(RuntimeError):

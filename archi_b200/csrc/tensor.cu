@@ -1142,6 +1142,8 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     if (*n_unverified_host > 0)
         ARCHI_CUDA(cudaMemcpy(unverified_host, w.unverified, (size_t)nq * 4, cudaMemcpyDeviceToHost));
     s->stats.grid = grid;
+    s->stats.coarse_dtype = tf32 ? ARCHI_F32 : ARCHI_BF16;
+    s->stats.coarse_launches = n_phases;
     return ARCHI_OK;
 }
 

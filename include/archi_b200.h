@@ -152,7 +152,11 @@ typedef struct {
     int passes;            /* corpus passes */
     int grid;              /* CTAs of the dominant kernel */
     int unverified_queries;/* tensor path: queries re-run on the exact path */
-    double last_kernel_ms; /* device time of the dominant kernel (CUDA events), if requested */
+    double last_kernel_ms; /* device time of the dominant kernel(s) (CUDA events), if requested: the scan
+                              kernel of one pass, or the tensor path's coarse launches + threshold kernels */
+    int coarse_dtype;      /* tensor path: element type the coarse pass read (ARCHI_BF16: bf16 rows or the
+                              bf16 shadow of fp32 rows; ARCHI_F32: fp32 rows as tf32) */
+    int coarse_launches;   /* tensor path: coarse-kernel launches per pass (warm-up phases + main) */
 } archi_search_stats_t;
 int archi_store_last_stats(archi_store_t *s, archi_search_stats_t *out);
 /* When enabled, archi_search brackets its dominant kernel with CUDA events on the caller's
