@@ -41,6 +41,16 @@ WORKLOADS = {
 METRIC = "queries_per_sec_exact_top10"
 
 
+def profiled_traffic(kernel, workload, batch):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        ent = json.load(open(p)).get(f"{kernel}|{workload}|{batch}")
+        return ent["traffic_bytes"] if ent else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -249,7 +259,8 @@ def main():
             algo_bytes = cnt * dim * elt + nq_launch * dim * 4 + nq_launch * k * 8
             ach = algo_bytes / (launch_ms * 1e-3) / 1e9
             return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                    "frac": ach / peaks["hbm_gbs"],
+                    "traffic": profiled_traffic("scan_topk_kernel", args.workload, nq_all) if world == 1 else None,
                     "peak_source": peaks["source"] + " hbm_gbs (copy, burst)", "kernel": "scan_topk_kernel",
                     "launch_ms": launch_ms, "algorithmic_bytes_per_launch": algo_bytes,
                     "launches_per_step": st.passes, "grid": st.grid, "frac_of_nominal_8TBps": ach / 8000.0}
@@ -266,7 +277,8 @@ def main():
         kname = "tc_coarse_kernel<bf16>" if st.coarse_dtype == N.BF16 else "tc_coarse_kernel<tf32>"
         if st.coarse_launches > 1:
             kname += f" x{st.coarse_launches} (warm-up phases + main) + tc_threshold_kernel x{st.coarse_launches - 1}, timed together"
-        common = {"traffic": None, "kernel": kname, "coarse_reads": "bf16 shadow of the fp32 rows" if (storage == "f32" and st.coarse_dtype == N.BF16) else storage + " rows",
+        common = {"traffic": profiled_traffic("tc_coarse_kernel", args.workload, nq_all) if world == 1 else None,
+                  "kernel": kname, "coarse_reads": "bf16 shadow of the fp32 rows" if (storage == "f32" and st.coarse_dtype == N.BF16) else storage + " rows",
                   "launch_ms": launch_ms, "algorithmic_bytes_per_launch": algo_bytes,
                   "algorithmic_flops_per_launch": algo_flops, "launches_per_step": st.passes, "grid": st.grid,
                   "achieved_GBps": gbs, "achieved_TFLOPs": tfs, "frac_hbm": gbs / peaks["hbm_gbs"],
