@@ -37,8 +37,9 @@ WORKLOADS = {
     "c2": (1_000_000, 384, "f32", 10, 1024, "configs[1]: synthetic 1M x 384 fp32 unit-norm chunks, top-10"),
     "c3": (10_000_000, 768, "bf16", 10, 1024, "configs[2]: synthetic 10M x 768 bf16 chunks, top-10, row-sharded"),
     "c4s": (12_500_000, 1024, "bf16", 100, 1024, "configs[3] one shard: 12.5M x 1024 bf16 chunks per GPU (of 100M over 8), top-100"),
+    "c4": (100_000_000, 1024, "bf16", 100, 1024, "configs[3]: synthetic 100M x 1024 bf16 chunks (204.8 GB) row-sharded, top-100"),
 }
-METRIC = "queries_per_sec_exact_top10"
+METRIC = "queries_per_sec_exact_top10"   # top-100 for the c4 workloads (config.k says which)
 
 
 def profiled_traffic(kernel, workload, batch):
@@ -170,7 +171,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sub-batches", default="1,64", help="extra batch sizes reported under 'batches' at N=1")
+    ap.add_argument("--sub-batches", default=None,
+                    help="extra batch sizes reported under 'batches' (default: 1,64 at N=1, none at N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rows, dim, storage, k, dbatch, desc = WORKLOADS[args.workload]
@@ -198,7 +200,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg_id = {"c2": 2, "c3": 3, "c4s": 4}[args.workload]
+    cfg_id = {"c2": 2, "c3": 3, "c4s": 4, "c4": 4}[args.workload]
+    if args.sub_batches is None:
+        args.sub_batches = "1,64" if world == 1 else ""
     # strong scaling: the corpus is fixed, rank r holds rows [first, first+cnt)
     total_rows = rows
     first, cnt = plan_row_shards(total_rows, world)[rank]
@@ -327,7 +331,7 @@ def main():
     ms_e2e = time_e2e(q_dev.cpu().numpy(), args.steps, args.warmup)
 
     batches = {}
-    if world == 1 and args.sub_batches:
+    if args.sub_batches:
         for qb in [int(b) for b in args.sub_batches.split(",") if b]:
             if qb == batch:
                 continue
