@@ -198,6 +198,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
 
     cfg_id = {"c2": 2, "c3": 3, "c4s": 4, "c4": 4}[args.workload]
