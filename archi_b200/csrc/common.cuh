@@ -48,7 +48,7 @@ extern std::atomic<int64_t> g_launches;
 constexpr int kMaxListK = 128;     // entries a warp-register list holds (4 per lane)
 constexpr int kScanThreads = 256;  // 8 warps per CTA
 constexpr int kMaxQB = 8;          // queries per corpus pass on the streaming path
-constexpr int kTensorMinBatch = 9; // ARCHI_PATH_AUTO: batches at least this large take the tensor path
+constexpr int kTensorMinBatch = 2; // ARCHI_PATH_AUTO: batches at least this large take the tensor path (measured crossover)
 constexpr int kTensorMaxBatch = 2048;  // queries per tensor-path launch (16 query tiles)
 
 struct Workspace {

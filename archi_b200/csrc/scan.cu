@@ -345,65 +345,73 @@ struct FinalizeParams {
     int *cursor_id_out;
 };
 
-template <int M>
+// Radix select instead of list insertion: the grid*k candidate keys are staged in shared memory,
+// the k-th largest key T is found in four 8-bit passes, everything above T survives together with
+// the lowest-id entries equal to T, and the <= k survivors are ranked by (key desc, id asc).
+constexpr int kFinKeep = kMaxListK;      // survivors (k <= 128)
+constexpr int kFinEq = 1024;             // entries tying the k-th key that are considered for the tie rule
+
 __global__ void __launch_bounds__(kScanThreads) scan_finalize_kernel(const FinalizeParams p)
 {
-    constexpr int WARPS = kScanThreads / 32;
-    constexpr int LEN = 32 * M;
-    __shared__ float skey[WARPS * LEN];
-    __shared__ int sid[WARPS * LEN];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ uint32_t s_keys[];             // [grid * k] mapped keys
+    __shared__ int s_hist[256];
+    __shared__ int s_misc[4];
+    __shared__ int s_nk, s_ne;
+    __shared__ float s_skey[kFinKeep];
+    __shared__ int s_sid[kFinKeep];
+    __shared__ int s_eid[kFinEq];
+    const int tid = threadIdx.x;
     const int q = blockIdx.x;
-
-    WarpTopK<M> mine;
-    mine.init();
-    float tk = -CUDART_INF_F;
-    int ti = INT_MAX;
     const int total = p.grid * p.k;
-    // flat walk over (list, rank) with 4 independent loads in flight per lane
-    for (int base = warp * 32 * 4; base < total; base += WARPS * 32 * 4) {
-        float ek[4];
-        int ei[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * 32 + lane;
-            ek[u] = -CUDART_INF_F;
-            ei[u] = INT_MAX;
-            if (i < total) {
-                const int b = i / p.k, r = i - b * p.k;
-                const size_t off = ((size_t)b * kMaxQB + q) * kMaxListK + r;
-                ek[u] = p.part_key[off];
-                ei[u] = p.part_id[off];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            unsigned cand = __ballot_sync(kFull, better(ek[u], ei[u], tk, ti));
-            while (cand) {
-                const int src = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const float nk = __shfl_sync(kFull, ek[u], src);
-                const int ni = __shfl_sync(kFull, ei[u], src);
-                if (mine.insert(nk, ni, p.k, lane)) mine.threshold(p.k, tk, ti);
-            }
-        }
+    auto slot_of = [&](int i) {
+        const int b = i / p.k, r = i - b * p.k;
+        return ((size_t)b * kMaxQB + q) * kMaxListK + r;
+    };
+    if (tid == 0) {
+        s_nk = 0;
+        s_ne = 0;
     }
-#pragma unroll
-    for (int s = 0; s < M; ++s) {
-        skey[warp * LEN + s * 32 + lane] = mine.key[s];
-        sid[warp * LEN + s * 32 + lane] = mine.id[s];
+#pragma unroll 4
+    for (int i = tid; i < total; i += kScanThreads) s_keys[i] = fmap(p.part_key[slot_of(i)]);
+    __syncthreads();
+    const int kk = p.k < total ? p.k : total;
+    int n_gt = 0;
+    const uint32_t T = block_radix_kth(s_keys, total, kk, s_hist, s_misc, n_gt);
+    const int need_eq = kk - n_gt;
+
+    // survivors: key > T, and the need_eq lowest ids among key == T
+    for (int i = tid; i < total; i += kScanThreads) {
+        const uint32_t u = s_keys[i];
+        if (u > T) {
+            const int s = atomicAdd(&s_nk, 1);
+            s_skey[s] = funmap(u);
+            s_sid[s] = p.part_id[slot_of(i)];
+        } else if (u == T) {
+            const int s = atomicAdd(&s_ne, 1);
+            if (s < kFinEq) s_eid[s] = p.part_id[slot_of(i)];
+        }
     }
     __syncthreads();
-    if (warp != 0) return;
-    WarpTopK<M> res;
-    res.init();
-    merge_staged<M>(skey, sid, WARPS, p.k, lane, res);
-#pragma unroll
-    for (int s = 0; s < M; ++s) {
-        const int rank = s * 32 + lane;
-        if (rank < p.k) {
-            const float key = res.key[s];
-            const int id = res.id[s];
+    const int ne = s_ne < kFinEq ? s_ne : kFinEq;
+    for (int i = tid; i < ne; i += kScanThreads) {
+        const int mine = s_eid[i];
+        int rank = 0;
+        for (int j = 0; j < ne; ++j) rank += (s_eid[j] < mine || (s_eid[j] == mine && j < i)) ? 1 : 0;
+        if (rank < need_eq) {
+            s_skey[n_gt + rank] = funmap(T);
+            s_sid[n_gt + rank] = mine;
+        }
+    }
+    __syncthreads();
+    const int nk = n_gt + (need_eq < ne ? need_eq : ne);
+
+    for (int i = tid; i < p.k; i += kScanThreads) {
+        if (i < nk) {
+            const float key = s_skey[i];
+            const int id = s_sid[i];
+            int rank = 0;
+            for (int j = 0; j < nk; ++j)
+                rank += (better(s_skey[j], s_sid[j], key, id) || (s_skey[j] == key && s_sid[j] == id && j < i)) ? 1 : 0;
             const bool empty = id == INT_MAX;
             float score;
             if (empty) score = CUDART_NAN_F;
@@ -416,6 +424,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_finalize_kernel(const Final
             if (rank == p.k - 1 && p.cursor_key_out) {
                 p.cursor_key_out[q] = key;
                 p.cursor_id_out[q] = id;
+            }
+        } else {
+            const size_t o = (size_t)q * p.k_total + p.col0 + i;
+            p.out_scores[o] = CUDART_NAN_F;
+            p.out_ids[o] = -1ll;
+            if (i == p.k - 1 && p.cursor_key_out) {
+                p.cursor_key_out[q] = -CUDART_INF_F;
+                p.cursor_id_out[q] = INT_MAX;
             }
         }
     }
@@ -532,10 +548,11 @@ int launch_scan_finalize(archi_store *s, const ScanArgs &a, int grid, int k_tota
     p.id_offset = id_offset;
     p.cursor_key_out = cursor_key_out;
     p.cursor_id_out = cursor_id_out;
-    if (a.k <= 32)
-        scan_finalize_kernel<1><<<a.nqb, kScanThreads, 0, st>>>(p);
-    else
-        scan_finalize_kernel<4><<<a.nqb, kScanThreads, 0, st>>>(p);
+    const size_t smem = (size_t)grid * a.k * sizeof(uint32_t);
+    ARCHI_REQUIRE(smem <= 200 * 1024, "scan_finalize: %zu B of candidate keys do not fit in shared memory", smem);
+    if (smem > 40 * 1024)
+        ARCHI_CUDA(cudaFuncSetAttribute((const void *)scan_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scan_finalize_kernel<<<a.nqb, kScanThreads, smem, st>>>(p);
     ARCHI_CHECK_LAUNCH();
     return ARCHI_OK;
 }

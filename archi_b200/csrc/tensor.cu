@@ -44,16 +44,6 @@ constexpr int MAX_QT = 16;         // query tiles per launch (2048 queries)
 constexpr int AUX_BYTES = EPI_WARPS * BN * 8;       // a private (a, b) tile copy per epilogue warp
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + AUX_BYTES + 256;
 
-// order-preserving map float -> uint32 (larger float <=> larger uint)
-__device__ __forceinline__ uint32_t fmap(float f)
-{
-    const uint32_t b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float funmap(uint32_t u)
-{
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
 // shared threshold word: 0 = "no threshold published yet"
 __device__ __forceinline__ float thr_from_word(uint32_t u) { return u ? funmap(u) : -CUDART_INF_F; }
 

@@ -107,6 +107,73 @@ __device__ __forceinline__ float warp_multi_reduce(float (&v)[NV], int lane)
     return x;
 }
 
+// order-preserving map float -> uint32 (larger float <=> larger uint) and back
+__device__ __forceinline__ uint32_t fmap(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float funmap(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// Block-level radix select over `total` uint32 keys in shared memory: returns the k-th largest key
+// (k >= 1, k <= total) and, through n_gt, how many keys are strictly larger.  MSB first, 8 bits per
+// pass; s_hist[256] and s_misc[4] are shared scratch.  Every thread of the block must call it.
+__device__ __forceinline__ uint32_t block_radix_kth(const uint32_t *keys, int total, int k, int *s_hist, int *s_misc,
+                                                   int &n_gt)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    uint32_t prefix = 0u, known = 0u;
+    int need = k, above_total = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 256; i += nthr) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < total; i += nthr) {
+            const uint32_t key = keys[i];
+            if ((key & known) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mine += s_hist[lane * 8 + j];
+            int suf = mine;   // inclusive suffix sum over lanes (higher lanes = larger digits)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_down_sync(kFull, suf, d);
+                if (lane + d < 32) suf += o;
+            }
+            const int above = suf - mine;
+            const unsigned who = __ballot_sync(kFull, above < need && suf >= need);
+            if (lane == __ffs(who) - 1) {
+                int acc = above, digit = lane * 8;
+                for (int j = 7; j >= 0; --j) {
+                    const int h = s_hist[lane * 8 + j];
+                    if (acc + h >= need) {
+                        digit = lane * 8 + j;
+                        break;
+                    }
+                    acc += h;
+                }
+                s_misc[1] = digit;
+                s_misc[2] = need - acc;   // rank inside the chosen bin
+                s_misc[3] = acc;          // keys of this prefix bucket that are above the chosen bin
+            }
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s_misc[1] << shift;
+        known |= 255u << shift;
+        need = s_misc[2];
+        above_total += s_misc[3];
+        __syncthreads();
+    }
+    n_gt = above_total;
+    return prefix;
+}
+
 template <int NV>
 struct Log2 {
     static constexpr int value = 1 + Log2<NV / 2>::value;

@@ -129,8 +129,8 @@ def test_auto_path_switches_by_batch_size():
     rng = np.random.default_rng(8)
     corpus = unit_rows(rng, 9000, 64)
     s = make_store(corpus)
-    s.search(unit_rows(rng, 4, 64), 5)
-    assert s.last_stats().path == 1                            # streaming for small batches
+    s.search(unit_rows(rng, 1, 64), 5)
+    assert s.last_stats().path == 1                            # streaming for a single query
     sc_t, id_t = s.search(unit_rows(rng, 64, 64), 5)
     assert s.last_stats().path == TENSOR
     # hybrid and k > 128 stay on the streaming path
