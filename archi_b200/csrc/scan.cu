@@ -354,8 +354,8 @@ constexpr int kFinEq = 1024;             // entries tying the k-th key that are 
 __global__ void __launch_bounds__(kScanThreads) scan_finalize_kernel(const FinalizeParams p)
 {
     extern __shared__ uint32_t s_keys[];             // [grid * k] mapped keys
-    __shared__ int s_hist[256];
-    __shared__ int s_misc[4];
+    __shared__ int s_hist[256 * (kScanThreads / 32)];
+    __shared__ int s_misc[8];
     __shared__ int s_nk, s_ne;
     __shared__ float s_skey[kFinKeep];
     __shared__ int s_sid[kFinKeep];

@@ -627,7 +627,7 @@ __device__ __forceinline__ size_t sel_list_base(const SelCommon &c, int l, int q
     return ((size_t)((l >> 1) * c.qt_count + qt)) * 2 + (l & 1);
 }
 
-constexpr int SEL_STAGE = 10240;   // keys staged in shared memory for the radix passes when they fit
+constexpr int SEL_STAGE = 8192;   // keys staged in shared memory for the radix passes when they fit
 
 // s_cnt[320], s_hist[256], s_misc[4], s_stage[SEL_STAGE] are shared-memory scratch; returns T, total via total_out
 __device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int q, int *s_cnt, int *s_hist, int *s_misc,
@@ -667,27 +667,23 @@ __device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int 
             }
         }
         __syncthreads();
+        int n_gt;
+        return block_radix_kth(s_stage, total, c.kprime, s_hist, s_misc, n_gt);
     }
 
+    // too many candidates to stage (rare): the same selection, re-walking the lists in global memory
     uint32_t prefix = 0u, known = 0u;   // bits of T fixed so far / their mask
     int need = c.kprime;                // rank still to be located inside the current prefix bucket
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         for (int i = tid; i < 256; i += SEL_THREADS) s_hist[i] = 0;
         __syncthreads();
-        if (staged) {
-            for (int i = tid; i < total; i += SEL_THREADS) {
-                const uint32_t key = s_stage[i];
+        for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
+            const int n = s_cnt[l];
+            const uint2 *src = c.cand + (sel_list_base(c, l, qt) * BM + tq) * c.cap;
+            for (int i = lane; i < n; i += 32) {
+                const uint32_t key = fmap(__uint_as_float(src[i].x));
                 if ((key & known) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
-            }
-        } else {
-            for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
-                const int n = s_cnt[l];
-                const uint2 *src = c.cand + (sel_list_base(c, l, qt) * BM + tq) * c.cap;
-                for (int i = lane; i < n; i += 32) {
-                    const uint32_t key = fmap(__uint_as_float(src[i].x));
-                    if ((key & known) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
-                }
             }
         }
         __syncthreads();
@@ -741,8 +737,8 @@ struct ThresholdParams {
 __global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const ThresholdParams p)
 {
     __shared__ int s_cnt[320];
-    __shared__ int s_hist[256];
-    __shared__ int s_misc[4];
+    __shared__ int s_hist[256 * (SEL_THREADS / 32)];
+    __shared__ int s_misc[8];
     __shared__ uint32_t s_stage[SEL_STAGE];
     int total;
     const uint32_t T = sel_radix_threshold(p.c, blockIdx.x, s_cnt, s_hist, s_misc, s_stage, total);
@@ -752,8 +748,8 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const Thresho
 __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
 {
     __shared__ int s_cnt[320];                      // per-list sizes (2 * ngroups <= 296)
-    __shared__ int s_hist[256];
-    __shared__ int s_misc[4];
+    __shared__ int s_hist[256 * (SEL_THREADS / 32)];
+    __shared__ int s_misc[8];
     __shared__ uint32_t s_stage[SEL_STAGE];
     __shared__ int s_nk;
     __shared__ uint32_t s_kid[KEPT_MAX];
@@ -794,20 +790,43 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     const bool overflow = s_nk > KEPT_MAX;          // more ties at T than we can hold: cannot prove
     const int nk = overflow ? KEPT_MAX : s_nk;
 
-    // exact fp32 rescoring, one warp per candidate
+    // exact fp32 rescoring, one warp per candidate: the query sits in shared memory (zero padded to
+    // the row stride), the stored row is read with 16-byte loads
+    extern __shared__ __align__(16) float s_q[];      // [ld]
     const QInfo qi = p.qinfo[q];
-    const float *qv = p.queries + (size_t)q * p.dim;
+    for (int e = tid; e < p.ld; e += SEL_THREADS) s_q[e] = e < p.dim ? p.queries[(size_t)q * p.dim + e] : 0.f;
+    __syncthreads();
+    const int vec = p.dtype == ARCHI_BF16 ? 8 : 4;
+    const int nvec = p.ld / vec;
     for (int c = warp; c < nk; c += SEL_THREADS / 32) {
         const size_t row = s_kid[c];
+        const uint4 *rp = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(p.corpus) +
+                                                          row * p.ld * (p.dtype == ARCHI_BF16 ? 2 : 4));
         float acc = 0.f;
-        for (int e = lane; e < p.dim; e += 32) {
-            const float x = row_elem(p.corpus, p.dtype, row * p.ld + e);
-            const float y = qv[e];
-            if (p.metric == ARCHI_L2) {
-                const float d = x - y;
-                acc = fmaf(d, d, acc);
+        for (int v = lane; v < nvec; v += 32) {
+            const uint4 d = __ldg(rp + v);
+            float x[8];
+            if (p.dtype == ARCHI_BF16) {
+                x[0] = __uint_as_float(d.x << 16); x[1] = __uint_as_float(d.x & 0xffff0000u);
+                x[2] = __uint_as_float(d.y << 16); x[3] = __uint_as_float(d.y & 0xffff0000u);
+                x[4] = __uint_as_float(d.z << 16); x[5] = __uint_as_float(d.z & 0xffff0000u);
+                x[6] = __uint_as_float(d.w << 16); x[7] = __uint_as_float(d.w & 0xffff0000u);
             } else {
-                acc = fmaf(x, y, acc);
+                x[0] = __uint_as_float(d.x); x[1] = __uint_as_float(d.y);
+                x[2] = __uint_as_float(d.z); x[3] = __uint_as_float(d.w);
+                x[4] = x[5] = x[6] = x[7] = 0.f;
+            }
+            const float *qq = s_q + v * vec;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < vec) {
+                    if (p.metric == ARCHI_L2) {
+                        const float t = x[i] - qq[i];
+                        acc = fmaf(t, t, acc);
+                    } else {
+                        acc = fmaf(x[i], qq[i], acc);
+                    }
+                }
             }
         }
 #pragma unroll
@@ -1067,7 +1086,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     int bounds[4] = {0, 0, 0, 0};
     int n_phases = 1;
     if (warm && n_ctiles >= 8 * ngroups) {
-        bounds[n_phases++] = 2 * ngroups < 40 ? 2 * ngroups : 40;   // <= 40 x 256 keys per query: staged select
+        bounds[n_phases++] = 2 * ngroups < 32 ? 2 * ngroups : 32;   // <= 32 x 256 keys per query: staged select
         if (n_ctiles >= 48 * ngroups) bounds[n_phases++] = round_up(n_ctiles / 16, 2 * ngroups);
     }
     bounds[n_phases] = n_ctiles;
@@ -1123,7 +1142,9 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     sp.id_offset = id_offset;
     sp.unverified = w.unverified;
     sp.n_unverified = w.unverified + nq_pad;
-    tc_select_kernel<<<nq, SEL_THREADS, 0, st>>>(sp);
+    const size_t q_smem = (size_t)s->ld * sizeof(float);
+    ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_smem));
+    tc_select_kernel<<<nq, SEL_THREADS, q_smem, st>>>(sp);
     ARCHI_CHECK_LAUNCH();
 
     // ---- the proof's verdict (4 bytes + flags) ----

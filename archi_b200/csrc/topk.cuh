@@ -119,21 +119,58 @@ __device__ __forceinline__ float funmap(uint32_t u)
 }
 
 // Block-level radix select over `total` uint32 keys in shared memory: returns the k-th largest key
-// (k >= 1, k <= total) and, through n_gt, how many keys are strictly larger.  MSB first, 8 bits per
-// pass; s_hist[256] and s_misc[4] are shared scratch.  Every thread of the block must call it.
+// (1 <= k <= total) and, through n_gt, how many keys are strictly larger.  The bits above the
+// highest bit in which the smallest and largest key differ are skipped (scores cluster in a narrow
+// band, so the top byte(s) are usually common and would serialise every histogram update on one
+// bin); below that, 8 bits per pass, one private histogram per warp.  s_hist needs
+// 256 * (blockDim.x / 32) ints, s_misc 8 ints.  Every thread of the block must call it.
 __device__ __forceinline__ uint32_t block_radix_kth(const uint32_t *keys, int total, int k, int *s_hist, int *s_misc,
                                                    int &n_gt)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
-    uint32_t prefix = 0u, known = 0u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
+    // block min / max
+    uint32_t kmax = 0u, kmin = 0xffffffffu;
+    for (int i = tid; i < total; i += nthr) {
+        const uint32_t key = keys[i];
+        kmax = max(kmax, key);
+        kmin = min(kmin, key);
+    }
+    kmax = __reduce_max_sync(kFull, kmax);
+    kmin = __reduce_min_sync(kFull, kmin);
+    if (tid == 0) {
+        s_misc[4] = 0;
+        s_misc[5] = (int)0xffffffffu;
+    }
+    __syncthreads();
+    if (lane == 0) {
+        atomicMax(reinterpret_cast<unsigned int *>(&s_misc[4]), kmax);
+        atomicMin(reinterpret_cast<unsigned int *>(&s_misc[5]), kmin);
+    }
+    __syncthreads();
+    kmax = (uint32_t)s_misc[4];
+    kmin = (uint32_t)s_misc[5];
+    n_gt = 0;
+    if (kmax == kmin) return kmax;                       // all keys equal
+    int top = 32 - __clz(kmax ^ kmin);                   // bits [0, top) still have to be resolved
+    uint32_t known = top >= 32 ? 0u : ~((1u << top) - 1u);
+    uint32_t prefix = kmax & known;
     int need = k, above_total = 0;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        for (int i = tid; i < 256; i += nthr) s_hist[i] = 0;
+    while (top > 0) {
+        const int width = top < 8 ? top : 8;
+        const int shift = top - width;
+        const uint32_t dmask = (1u << width) - 1u;
+        for (int i = tid; i < 256 * nwarp; i += nthr) s_hist[i] = 0;
         __syncthreads();
+        int *myhist = s_hist + warp * 256;
         for (int i = tid; i < total; i += nthr) {
             const uint32_t key = keys[i];
-            if ((key & known) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+            if ((key & known) == prefix) atomicAdd(&myhist[(key >> shift) & dmask], 1);
+        }
+        __syncthreads();
+        for (int i = tid; i < 256; i += nthr) {          // fold the per-warp histograms into the first
+            int sum = 0;
+            for (int w = 0; w < nwarp; ++w) sum += s_hist[w * 256 + i];
+            s_hist[i] = sum;
         }
         __syncthreads();
         if (warp == 0) {
@@ -165,9 +202,10 @@ __device__ __forceinline__ uint32_t block_radix_kth(const uint32_t *keys, int to
         }
         __syncthreads();
         prefix |= (uint32_t)s_misc[1] << shift;
-        known |= 255u << shift;
+        known |= dmask << shift;
         need = s_misc[2];
         above_total += s_misc[3];
+        top = shift;
         __syncthreads();
     }
     n_gt = above_total;

@@ -264,3 +264,20 @@ def test_full_size_config2_properties():
         assert orc.same_topk_up_to_ties(id8[i].cpu().tolist(), iq[i], dq[i], rel_tol=2e-6, abs_tol=1e-7)
     assert np.allclose(sc8[:4].cpu().numpy(), 1.0 - dq, rtol=REL_F32, atol=1e-6)
     s.close()
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+@pytest.mark.parametrize("nq", [2, 3, 5, 8, 11])
+def test_streaming_path_multi_query_kernels(storage, nq):
+    """ARCHI_PATH_AUTO sends batches >= 2 to the tensor path; the multi-query streaming kernels
+    (QB = 2 / 4 / 8) still serve hybrid search and proof fallbacks, so they are pinned here."""
+    rng = np.random.default_rng(100 + nq)
+    corpus = unit_rows(rng, 15013, 200)
+    queries = unit_rows(rng, nq, 200)
+    for metric in ("cosine", "l2"):
+        s = make_store(corpus, metric, storage)
+        scores, ids = s.search(queries, 10, path=1)
+        assert s.last_stats().path == 1
+        check_against_truth(metric, stored_values(corpus, storage), queries, 10, scores, ids,
+                            REL_BF16 if storage == "bf16" else REL_F32)
+        s.close()
