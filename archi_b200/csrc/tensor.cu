@@ -33,16 +33,23 @@ namespace tc {
 
 constexpr int BM = 128;            // queries per tile (MMA M, TMEM lanes)
 constexpr int BN = 256;            // corpus rows per tile (MMA N, TMEM columns)
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * 128;  // one 128-byte swizzle row per query per K chunk
-constexpr int B_BYTES = BN * 128;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+// 1-CTA mode: a stage holds the whole 256-row corpus tile (48 KB, 4 stages); CTA-pair mode
+// (cta_group::2): each CTA holds its 128 queries and HALF of the corpus tile (32 KB, 6 stages)
+template <bool TWO> struct Geo {
+    static constexpr int B_ROWS = TWO ? BN / 2 : BN;
+    static constexpr int B_BYTES = B_ROWS * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = TWO ? 6 : 4;
+};
+constexpr int RING_BYTES = 4 * (A_BYTES + BN * 128);   // = 6 * (A_BYTES + BN/2 * 128) = 196608
+constexpr int MAX_STAGES = 6;
 constexpr int NTHREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..5 / 6..9 epilogue groups 0 / 1
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_QT = 16;         // query tiles per launch (2048 queries)
 constexpr int AUX_BYTES = EPI_WARPS * BN * 8;       // a private (a, b) tile copy per epilogue warp
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + AUX_BYTES + 256;
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + AUX_BYTES + 256;
 
 // shared threshold word: 0 = "no threshold published yet"
 __device__ __forceinline__ float thr_from_word(uint32_t u) { return u ? funmap(u) : -CUDART_INF_F; }
@@ -294,25 +301,32 @@ __device__ __forceinline__ void compact_dispatch(uint2 *buf, int n, int kprime, 
     else compact_buffer<32>(buf, n, kprime, lane, nc, nt);
 }
 
-template <bool TF32>
-__global__ void __launch_bounds__(NTHREADS, 1)
-tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
-                 const CoarseParams p)
+// TWO = CTA-pair mode: a cluster of two CTAs (an SM pair) scores 256 queries (128 per CTA) against
+// one 256-row corpus tile with tcgen05.mma.cta_group::2 (M = 256).  Each CTA loads its own query tile
+// and HALF of the corpus tile; the leader CTA (cluster rank 0) issues the MMAs for the pair, and each
+// CTA's epilogue drains its own TMEM.  Per SM this halves the corpus bytes written to and read from
+// shared memory, which is what bounds the 1-CTA kernel.
+template <bool TF32, bool TWO>
+__device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUtensorMap &tmap_c, const CoarseParams &p)
 {
+    constexpr int STAGES = Geo<TWO>::STAGES;
+    constexpr int STAGE_BYTES = Geo<TWO>::STAGE_BYTES;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = ptx::smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte aligned (128B swizzle atoms)
     unsigned char *base_ptr = smem_dyn + (base - raw);
     // layout: [STAGES x (A | B)] [aux: EPI_WARPS x BN float2] [barriers, tmem ptr: 256 B]
-    float2 *s_aux = reinterpret_cast<float2 *>(base_ptr + STAGES * STAGE_BYTES);
-    const uint32_t bar0 = base + STAGES * STAGE_BYTES + AUX_BYTES;
-    const uint32_t full_bar = bar0, empty_bar = bar0 + 8 * STAGES;
-    const uint32_t tfull_bar = bar0 + 16 * STAGES, tempty_bar = tfull_bar + 16;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + STAGES * STAGE_BYTES + AUX_BYTES + 16 * STAGES + 32);
+    float2 *s_aux = reinterpret_cast<float2 *>(base_ptr + RING_BYTES);
+    const uint32_t bar0 = base + RING_BYTES + AUX_BYTES;
+    const uint32_t full_bar = bar0, empty_bar = bar0 + 8 * MAX_STAGES;
+    const uint32_t tfull_bar = bar0 + 16 * MAX_STAGES, tempty_bar = tfull_bar + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + RING_BYTES + AUX_BYTES + 16 * MAX_STAGES + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x % p.qt_count;
+    const int qt = blockIdx.x % p.qt_count;                 // pair mode: qt_count is even, the pair is (2j, 2j+1)
     const int group = blockIdx.x / p.qt_count;
+    const uint32_t cta_rank = TWO ? ptx::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0u;
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&tmap_q);
@@ -323,18 +337,27 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull_bar + 8 * a, 1);
-            ptx::mbar_init(tempty_bar + 8 * a, 4);
+            ptx::mbar_init(tempty_bar + 8 * a, TWO ? 8 : 4);   // pair mode: both CTAs' epilogues release the leader
         }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (TWO) {
+            ptx::tmem_alloc_2sm(ptx::smem_u32(tmem_slot), TMEM_COLS);
+            ptx::tmem_relinquish_2sm();
+        } else {
+            ptx::tmem_alloc(ptx::smem_u32(tmem_slot), TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (TWO) ptx::cluster_sync();      // the peer's barriers must be initialised before anything signals them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // addresses of the LEADER's barriers as seen from this CTA
+    const uint32_t full_bar_leader = TWO ? ptx::mapa(full_bar, 0) : full_bar;
+    const uint32_t tempty_bar_leader = TWO ? ptx::mapa(tempty_bar, 0) : tempty_bar;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -344,10 +367,18 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int ct = p.tile_begin + group; ct < p.tile_end; ct += p.ngroups) {
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
-                    ptx::mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
                     const uint32_t sa = base + s * STAGE_BYTES;
-                    ptx::tma_load_2d(sa, &tmap_q, full_bar + 8 * s, kc * p.kelems, qt * BM);
-                    ptx::tma_load_2d(sa + A_BYTES, &tmap_c, full_bar + 8 * s, kc * p.kelems, ct * BN);
+                    if (TWO) {
+                        // the leader's barrier collects the bytes of both CTAs
+                        if (leader) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);
+                        ptx::tma_load_2d_2sm(sa, &tmap_q, full_bar_leader + 8 * s, kc * p.kelems, qt * BM);
+                        ptx::tma_load_2d_2sm(sa + A_BYTES, &tmap_c, full_bar_leader + 8 * s, kc * p.kelems,
+                                             ct * BN + (int)cta_rank * (BN / 2));
+                    } else {
+                        ptx::mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+                        ptx::tma_load_2d(sa, &tmap_q, full_bar + 8 * s, kc * p.kelems, qt * BM);
+                        ptx::tma_load_2d(sa + A_BYTES, &tmap_c, full_bar + 8 * s, kc * p.kelems, ct * BN);
+                    }
                     if (++s == STAGES) {
                         s = 0;
                         ph ^= 1u;
@@ -357,11 +388,12 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            // instruction descriptor: D fp32, A/B bf16 (1) or tf32 (2), both K-major, N = 256, M = 128
+        if (lane == 0 && leader) {
+            // instruction descriptor: D fp32, A/B bf16 (1) or tf32 (2), both K-major, N = 256,
+            // M = 128 (one CTA) or 256 (CTA pair)
             const uint32_t fmt = TF32 ? 2u : 1u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)(BM >> 4) << 24);
+                                   ((uint32_t)((TWO ? 2 * BM : BM) >> 4) << 24);
             int s = 0, u = 0;
             uint32_t ph = 0;
             for (int ct = p.tile_begin + group; ct < p.tile_end; ct += p.ngroups, ++u) {
@@ -380,18 +412,26 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     for (int k4 = 0; k4 < 4; ++k4) {
                         if (p.debug & 1) break;
                         // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-                        if (TF32)
-                            ptx::mma_tf32(tmem_d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kc | k4) ? 1u : 0u);
-                        else
-                            ptx::mma_bf16(tmem_d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kc | k4) ? 1u : 0u);
+                        const uint32_t accum = (kc | k4) ? 1u : 0u;
+                        if (TWO) {
+                            if (TF32) ptx::mma_tf32_2sm(tmem_d, adesc + 2 * k4, bdesc + 2 * k4, idesc, accum);
+                            else ptx::mma_bf16_2sm(tmem_d, adesc + 2 * k4, bdesc + 2 * k4, idesc, accum);
+                        } else {
+                            if (TF32) ptx::mma_tf32(tmem_d, adesc + 2 * k4, bdesc + 2 * k4, idesc, accum);
+                            else ptx::mma_bf16(tmem_d, adesc + 2 * k4, bdesc + 2 * k4, idesc, accum);
+                        }
                     }
-                    ptx::tc_commit(empty_bar + 8 * s);  // smem stage reusable once these MMAs retire
+                    // smem stage reusable (in both CTAs) once these MMAs retire
+                    if (TWO) ptx::tc_commit_2sm(empty_bar + 8 * s, 3);
+                    else ptx::tc_commit(empty_bar + 8 * s);
                     if (++s == STAGES) {
                         s = 0;
                         ph ^= 1u;
                     }
                 }
-                ptx::tc_commit(tfull_bar + 8 * acc);    // accumulator ready for the epilogue
+                // accumulator ready for the epilogue (of both CTAs in pair mode)
+                if (TWO) ptx::tc_commit_2sm(tfull_bar + 8 * acc, 3);
+                else ptx::tc_commit(tfull_bar + 8 * acc);
             }
         }
     } else {
@@ -535,7 +575,10 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // accumulator drained: hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * grp);
+            if (lane == 0) {
+                if (TWO) ptx::mbar_arrive_cluster(tempty_bar_leader + 8 * grp);
+                else ptx::mbar_arrive(tempty_bar + 8 * grp);
+            }
 
             // eager compaction keeps the thresholds tight (warp-collective, one owner lane at a time)
             unsigned need = __ballot_sync(kFull, cnt >= p.trigger);
@@ -574,11 +617,29 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (TWO) ptx::cluster_sync();      // neither CTA may leave while the other can still signal / read it
+    else __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (TWO) ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                 const CoarseParams p)
+{
+    coarse_body<TF32, false>(tmap_q, tmap_c, p);
+}
+
+template <bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+tc_coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                      const CoarseParams p)
+{
+    coarse_body<TF32, true>(tmap_q, tmap_c, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -962,7 +1023,11 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     const int kelems = tf32 ? 32 : 64;
     const int ldq = round_up(s->dim, tf32 ? 4 : 8);
     const int ld_sh = round_up(s->dim, 8);
-    const int qt_count = (nq + BM - 1) / BM;
+    // CTA-pair mode (cta_group::2) needs at least two query tiles; the tile count is padded to even
+    static const int pair_env = getenv("ARCHI_TC_PAIR") ? atoi(getenv("ARCHI_TC_PAIR")) : 1;
+    int qt_count = (nq + BM - 1) / BM;
+    const bool pair = pair_env != 0 && qt_count >= 2;
+    if (pair) qt_count = (qt_count + 1) & ~1;
     ARCHI_REQUIRE(qt_count <= MAX_QT, "tensor path: at most %d queries per launch", MAX_QT * BM);
     const int nq_pad = qt_count * BM;
     int kprime = k <= 10 ? 32 : round_up(2 * k + 12, 32);
@@ -1051,7 +1116,8 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     // ---- 3. coarse scorer ----
     CUtensorMap tmap_q, tmap_c;
     if ((rc = make_tmap(&tmap_q, w.qstage, tf32, nq_pad, ldq, BM)) != ARCHI_OK) return rc;
-    if ((rc = make_tmap(&tmap_c, use_shadow ? w.shadow : s->data, tf32, s->rows, use_shadow ? ld_sh : s->ld, BN)) != ARCHI_OK)
+    if ((rc = make_tmap(&tmap_c, use_shadow ? w.shadow : s->data, tf32, s->rows, use_shadow ? ld_sh : s->ld,
+                        pair ? BN / 2 : BN)) != ARCHI_OK)
         return rc;
     CoarseParams cp;
     cp.n = s->rows;
@@ -1073,7 +1139,8 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     cp.cand = reinterpret_cast<uint2 *>(w.cand);
     cp.cand_cnt = w.cand_cnt;
     cp.thr_g = w.thr_g;
-    auto kern = tf32 ? tc_coarse_kernel<true> : tc_coarse_kernel<false>;
+    auto kern = pair ? (tf32 ? tc_coarse_pair_kernel<true> : tc_coarse_pair_kernel<false>)
+                     : (tf32 ? tc_coarse_kernel<true> : tc_coarse_kernel<false>);
     ARCHI_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     // Warm-up phases.  Thresholds local to one (CTA, epilogue group) only ever see 1/(2*ngroups) of
     // the rows, so most of a plain run is spent storing candidates that a global view would reject.
