@@ -76,7 +76,8 @@ struct TensorWorkspace {
     void *cand = nullptr;        size_t cand_bytes = 0;     // [grid][128][cap] candidates
     int *cand_cnt = nullptr;     size_t cnt_bytes = 0;
     void *aux = nullptr;         size_t aux_bytes = 0;      // [capacity] (a, b) per row
-    float *max_norm2 = nullptr;
+    float *max_norm2 = nullptr;  // device [2]: max / min |row|^2 over live rows
+    float h_max_norm2 = 0.f, h_min_norm2 = 0.f;   // host copies (refreshed with maxnorm_epoch)
     // bf16 shadow of an fp32 store: the coarse pass reads it (half the bytes, full-rate MMA); the
     // exact rescoring still reads the fp32 rows
     void *shadow = nullptr;      size_t shadow_bytes = 0;

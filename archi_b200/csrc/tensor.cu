@@ -75,6 +75,8 @@ struct PrepParams {
     int *unverified;       // [nq]
     const float *max_norm2;// [1] max |row|^2 over the store
     float corpus_rel_err;  // 2^-9 when the coarse pass reads a bf16 shadow of fp32 rows, else 0
+    int cos_raw_unnorm;    // cosine scored as a raw dot over rows that are only approximately unit length
+    float norm_dev;        // max |1/|c| - 1| over the store (cos_raw_unnorm)
 };
 
 __global__ void __launch_bounds__(128) tc_prep_kernel(const PrepParams p)
@@ -117,7 +119,8 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(const PrepParams p)
         unit += (float)p.dim * 2.4e-7f * qn;
         const float maxn = sqrtf(*p.max_norm2);
         float eps;
-        if (p.metric == ARCHI_COSINE) eps = unit;                 // key = dot / |c|
+        if (p.metric == ARCHI_COSINE && p.cos_raw_unnorm) eps = (unit + qn * p.norm_dev * 1.001f) * maxn;  // key = dot
+        else if (p.metric == ARCHI_COSINE) eps = unit;            // key = dot / |c|
         else if (p.metric == ARCHI_IP) eps = unit * maxn;         // key = dot
         else eps = 2.f * unit * maxn + 1e-6f * maxn * maxn;       // key = 2 dot - |c|^2
         QInfo qi;
@@ -157,24 +160,42 @@ __global__ void tc_aux_kernel(float2 *aux, const float *norm2, const uint32_t *a
 }
 
 // fp32 rows -> bf16 shadow rows (row strides ld_src / ld_dst elements, padding zeroed)
+// With `norm2` (cosine stores) the shadow rows are scaled to unit length, so that the coarse key of
+// the cosine metric is the raw dot product.
 __global__ void tc_shadow_kernel(const float *src, __nv_bfloat16 *dst, long long first, long long n, int dim,
-                                 int ld_src, int ld_dst)
+                                 int ld_src, int ld_dst, const float *norm2)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * ld_dst) return;
     const long long r = first + i / ld_dst;
     const int e = (int)(i % ld_dst);
-    dst[r * ld_dst + e] = __float2bfloat16_rn(e < dim ? src[r * ld_src + e] : 0.f);
+    float v = e < dim ? src[r * ld_src + e] : 0.f;
+    if (norm2) {
+        const float n2 = norm2[r];
+        v = n2 > 0.f ? v * (1.0f / sqrtf(n2)) : 0.f;
+    }
+    dst[r * ld_dst + e] = __float2bfloat16_rn(v);
 }
 
-__global__ void tc_maxnorm_kernel(const float *norm2, long long n, float *out)
+// out[0] = max |row|^2, out[1] = min |row|^2 over live rows (non-negative floats order like their bits)
+__global__ void tc_maxnorm_kernel(const float *norm2, const uint32_t *alive, long long n, float *out)
 {
-    float m = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        m = fmaxf(m, norm2[i]);
+    float m = 0.f, mn = CUDART_INF_F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (alive && !((alive[i >> 5] >> (i & 31)) & 1u)) continue;
+        const float v = norm2[i];
+        m = fmaxf(m, v);
+        mn = fminf(mn, v);
+    }
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, d));
-    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m));
+    for (int d = 16; d >= 1; d >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(kFull, m, d));
+        mn = fminf(mn, __shfl_xor_sync(kFull, mn, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m));
+        atomicMin(reinterpret_cast<unsigned int *>(out + 1), __float_as_uint(mn));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -195,7 +216,9 @@ struct CoarseParams {
     int resume;           // 1: continue from the candidate counts / thresholds left by a previous launch
     int debug;            // profiling aid (ARCHI_TC_DEBUG): 1 = skip the MMAs, 2 = skip the epilogue math
     int exit_cap;         // buffers larger than this are compacted before the CTA exits
-    const float2 *aux;    // [n]
+    const float2 *aux;    // [n] (a, b) per row -- aux mode only
+    const uint32_t *alive;   // raw mode: tombstone bitmask (may be null)
+    const uint32_t *filter;  // raw mode: per-search filter bitmask (may be null)
     uint2 *cand;          // [grid][BM][cap]  (key bits, row id)
     int *cand_cnt;        // [grid][BM]
     uint32_t *thr_g;      // [nq]
@@ -306,7 +329,10 @@ __device__ __forceinline__ void compact_dispatch(uint2 *buf, int n, int kprime, 
 // and HALF of the corpus tile; the leader CTA (cluster rank 0) issues the MMAs for the pair, and each
 // CTA's epilogue drains its own TMEM.  Per SM this halves the corpus bytes written to and read from
 // shared memory, which is what bounds the 1-CTA kernel.
-template <bool TF32, bool TWO>
+// RAW = the coarse key is the raw dot product (inner product; cosine over unit-norm rows): no per-column
+// constants, masked rows are cleared with one bitmask word per 32 columns, and a chunk whose maximum
+// does not beat the thresholds of any lane is skipped after a 3-input max tree.
+template <bool TF32, bool TWO, bool RAW>
 __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUtensorMap &tmap_c, const CoarseParams &p)
 {
     constexpr int STAGES = Geo<TWO>::STAGES;
@@ -469,11 +495,23 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
         for (int ct = p.tile_begin + group + grp * p.ngroups; ct < p.tile_end; ct += 2 * p.ngroups, u += 2) {
             const uint32_t aph = (uint32_t)(u >> 1) & 1u;
             // this tile's per-row constants, fetched while the MMAs run (warp-private: no CTA barrier)
-            __syncwarp();
+            uint32_t tile_word = 0u;                 // raw mode: lane j < 8 holds the live-row bits of chunk j
+            if (RAW) {
+                if (lane < BN / 32) {
+                    const long long r0 = (long long)ct * BN + lane * 32;
+                    if (r0 < p.n) {
+                        tile_word = r0 + 32 <= p.n ? 0xffffffffu : ((1u << (int)(p.n - r0)) - 1u);
+                        if (p.alive) tile_word &= __ldg(p.alive + (r0 >> 5));
+                        if (p.filter) tile_word &= __ldg(p.filter + (r0 >> 5));
+                    }
+                }
+            } else {
+                __syncwarp();
 #pragma unroll
-            for (int i = 0; i < BN / 32; ++i) {
-                const long long r = (long long)ct * BN + i * 32 + lane;
-                aux_w[i * 32 + lane] = r < p.n ? __ldg(p.aux + r) : make_float2(0.f, -CUDART_INF_F);
+                for (int i = 0; i < BN / 32; ++i) {
+                    const long long r = (long long)ct * BN + i * 32 + lane;
+                    aux_w[i * 32 + lane] = r < p.n ? __ldg(p.aux + r) : make_float2(0.f, -CUDART_INF_F);
+                }
             }
             if (active) thr = fmaxf(thr, thr_from_word(__ldcg(p.thr_g + q)));
             __syncwarp();
@@ -489,12 +527,29 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
             //      (compaction trigger), so a tile cannot overflow the buffer.
             auto process = [&](uint32_t (&r)[32], int c) {
                 uint32_t mask = 0u;
+                if (RAW) {
+                    // chunk maximum first: most chunks of the main phase beat no lane's threshold
+                    float m[11];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 ab = aux_w[c * 32 + j];
-                    const float key = fmaf(__uint_as_float(r[j]), ab.x, ab.y);
-                    r[j] = __float_as_uint(key);
-                    mask |= (key > thr) ? (1u << j) : 0u;
+                    for (int j = 0; j < 10; ++j)
+                        m[j] = fmaxf(fmaxf(__uint_as_float(r[3 * j]), __uint_as_float(r[3 * j + 1])), __uint_as_float(r[3 * j + 2]));
+                    m[10] = fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+                    const float m0 = fmaxf(fmaxf(m[0], m[1]), m[2]), m1 = fmaxf(fmaxf(m[3], m[4]), m[5]);
+                    const float m2 = fmaxf(fmaxf(m[6], m[7]), m[8]), m3 = fmaxf(m[9], m[10]);
+                    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    if (!__any_sync(kFull, mx > thr)) return;
+                    const uint32_t live = __shfl_sync(kFull, tile_word, c);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) > thr) ? (1u << j) : 0u;
+                    mask &= live;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float2 ab = aux_w[c * 32 + j];
+                        const float key = fmaf(__uint_as_float(r[j]), ab.x, ab.y);
+                        r[j] = __float_as_uint(key);
+                        mask |= (key > thr) ? (1u << j) : 0u;
+                    }
                 }
                 // (2) columns admitted by ANY lane of the warp (few): visit them one by one; the column
                 //     index is warp-uniform, so picking the register is a uniform jump, and only the
@@ -626,20 +681,20 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
     }
 }
 
-template <bool TF32>
+template <bool TF32, bool RAW>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_coarse_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                  const CoarseParams p)
 {
-    coarse_body<TF32, false>(tmap_q, tmap_c, p);
+    coarse_body<TF32, false, RAW>(tmap_q, tmap_c, p);
 }
 
-template <bool TF32>
+template <bool TF32, bool RAW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 tc_coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const CoarseParams p)
 {
-    coarse_body<TF32, true>(tmap_q, tmap_c, p);
+    coarse_body<TF32, true, RAW>(tmap_q, tmap_c, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -897,7 +952,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
             if (p.metric == ARCHI_COSINE) {
                 const float n2 = p.norm2[row];
                 const float rn = n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f;
-                ex = acc * rn;                                       // coarse-key space: dot / |c|
+                ex = n2 > 0.f ? acc * rn : -CUDART_INF_F;            // coarse-key space: dot / |c|
                 sc = fminf(1.f, fmaxf(-1.f, acc * qi.rn_q * rn));
             } else if (p.metric == ARCHI_IP) {
                 ex = acc;
@@ -920,8 +975,9 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
         int rank = 0;
         for (int j = 0; j < nk; ++j) rank += better(s_ex[j], (int)s_kid[j], mine, mid) ? 1 : 0;
         if (rank < p.k) {
-            p.out_scores[(size_t)q * p.k + rank] = s_sc[i];
-            p.out_ids[(size_t)q * p.k + rank] = (long long)mid + p.id_offset;
+            const bool dead = mine == -CUDART_INF_F;              // zero-norm row under cosine: not a match
+            p.out_scores[(size_t)q * p.k + rank] = dead ? CUDART_NAN_F : s_sc[i];
+            p.out_ids[(size_t)q * p.k + rank] = dead ? -1ll : (long long)mid + p.id_offset;
         }
         if (rank == p.k - 1) ek = mine;
     }
@@ -1056,7 +1112,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         if ((rc = ensure_buf(&w.aux, &w.aux_bytes, need)) != ARCHI_OK) return rc;
         if (realloc) w.aux_epoch = -1;
     }
-    if (!w.max_norm2) ARCHI_CUDA(cudaMalloc(&w.max_norm2, 4));
+    if (!w.max_norm2) ARCHI_CUDA(cudaMalloc(&w.max_norm2, 8));
     if (use_shadow) {
         const size_t need = (size_t)s->capacity * ld_sh * 2;
         const bool realloc = !w.shadow || w.shadow_bytes < need;
@@ -1067,23 +1123,45 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
             const long long n_new = s->rows - w.shadow_rows;
             const long long tot = n_new * ld_sh;
             tc_shadow_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-                (const float *)s->data, (__nv_bfloat16 *)w.shadow, w.shadow_rows, n_new, s->dim, s->ld, ld_sh);
+                (const float *)s->data, (__nv_bfloat16 *)w.shadow, w.shadow_rows, n_new, s->dim, s->ld, ld_sh,
+                s->metric == ARCHI_COSINE ? s->norm2 : nullptr);
             ARCHI_CHECK_LAUNCH();
             w.shadow_rows = s->rows;
         }
     }
 
     // ---- cached per-store data: max |row|^2 and the (a, b) constants ----
+    const uint32_t *alive = include_deleted ? nullptr : s->alive;
     if (w.maxnorm_epoch != s->epoch) {
-        ARCHI_CUDA(cudaMemsetAsync(w.max_norm2, 0, 4, st));
-        tc_maxnorm_kernel<<<s->sm_count * 2, 256, 0, st>>>(s->norm2, s->rows, w.max_norm2);
+        const uint32_t init[2] = {0u, 0x7f800000u};   // max = 0, min = +inf
+        ARCHI_CUDA(cudaMemcpyAsync(w.max_norm2, init, 8, cudaMemcpyHostToDevice, st));
+        tc_maxnorm_kernel<<<s->sm_count * 2, 256, 0, st>>>(s->norm2, s->alive, s->rows, w.max_norm2);
         ARCHI_CHECK_LAUNCH();
+        float h[2];
+        ARCHI_CUDA(cudaMemcpyAsync(h, w.max_norm2, 8, cudaMemcpyDeviceToHost, st));
+        ARCHI_CUDA(cudaStreamSynchronize(st));
+        w.h_max_norm2 = h[0];
+        w.h_min_norm2 = h[1];
         w.maxnorm_epoch = s->epoch;
     }
-    const uint32_t *alive = include_deleted ? nullptr : s->alive;
+    // Raw-key epilogue (no per-column constants): inner product always; cosine when the rows the
+    // coarse pass reads are unit length -- exactly (normalised bf16 shadow of an fp32 store) or within
+    // a small, measured deviation that is added to the error bound (bf16 stores of unit-norm rows).
+    bool raw = false, cos_raw_unnorm = false;
+    float norm_dev = 0.f;
+    static const int raw_env = getenv("ARCHI_TC_RAW") ? atoi(getenv("ARCHI_TC_RAW")) : 1;
+    if (raw_env) {
+        if (s->metric == ARCHI_IP) raw = true;
+        else if (s->metric == ARCHI_COSINE && use_shadow) raw = true;
+        else if (s->metric == ARCHI_COSINE && w.h_min_norm2 > 0.f) {
+            const float d0 = fabsf(1.0f / sqrtf(w.h_min_norm2) - 1.0f), d1 = fabsf(1.0f / sqrtf(w.h_max_norm2) - 1.0f);
+            norm_dev = d0 > d1 ? d0 : d1;
+            if (norm_dev < 1.0f / 64.0f) raw = cos_raw_unnorm = true;
+        }
+    }
     const bool aux_cached = w.aux_epoch == s->epoch && w.aux_alive == (alive != nullptr) && filter == nullptr &&
                             !w.aux_had_filter;
-    if (!aux_cached) {
+    if (!raw && !aux_cached) {
         tc_aux_kernel<<<(unsigned)((s->rows + 255) / 256), 256, 0, st>>>(reinterpret_cast<float2 *>(w.aux), s->norm2, alive,
                                                                         filter, s->rows, s->metric);
         ARCHI_CHECK_LAUNCH();
@@ -1109,6 +1187,8 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     pp.unverified = w.unverified;
     pp.max_norm2 = w.max_norm2;
     pp.corpus_rel_err = use_shadow ? 0.001953125f : 0.f;
+    pp.cos_raw_unnorm = cos_raw_unnorm;
+    pp.norm_dev = norm_dev;
     ARCHI_CUDA(cudaMemsetAsync(w.unverified + nq_pad, 0, 4, st));
     tc_prep_kernel<<<nq, 128, 0, st>>>(pp);
     ARCHI_CHECK_LAUNCH();
@@ -1136,11 +1216,16 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     }
     cp.exit_cap = cap;           // final launch: nothing to bound (the select kernel walks global memory)
     cp.aux = reinterpret_cast<const float2 *>(w.aux);
+    cp.alive = alive;
+    cp.filter = filter;
     cp.cand = reinterpret_cast<uint2 *>(w.cand);
     cp.cand_cnt = w.cand_cnt;
     cp.thr_g = w.thr_g;
-    auto kern = pair ? (tf32 ? tc_coarse_pair_kernel<true> : tc_coarse_pair_kernel<false>)
-                     : (tf32 ? tc_coarse_kernel<true> : tc_coarse_kernel<false>);
+    void (*kern)(const CUtensorMap, const CUtensorMap, const CoarseParams);
+    if (pair) kern = tf32 ? (raw ? tc_coarse_pair_kernel<true, true> : tc_coarse_pair_kernel<true, false>)
+                          : (raw ? tc_coarse_pair_kernel<false, true> : tc_coarse_pair_kernel<false, false>);
+    else kern = tf32 ? (raw ? tc_coarse_kernel<true, true> : tc_coarse_kernel<true, false>)
+                     : (raw ? tc_coarse_kernel<false, true> : tc_coarse_kernel<false, false>);
     ARCHI_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     // Warm-up phases.  Thresholds local to one (CTA, epilogue group) only ever see 1/(2*ngroups) of
     // the rows, so most of a plain run is spent storing candidates that a global view would reject.
