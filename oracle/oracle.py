@@ -362,3 +362,62 @@ def c_pool_normalize(hidden: np.ndarray, mask: np.ndarray) -> np.ndarray:
     out = np.empty((B, H), dtype=np.float32)
     lib.orc_pool_normalize(_ptr(h), _ptr(m), B, L, H, _ptr(out))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# hnsw.c via ctypes: restated default index of the reference store (recall report only)
+# --------------------------------------------------------------------------------------------
+_HNSW = None
+
+
+def hnsw_lib() -> ctypes.CDLL:
+    global _HNSW
+    if _HNSW is None:
+        so = os.path.join(_HERE, f"libhnsw_{_cpu_tag()}.so")
+        src = os.path.join(_HERE, "hnsw.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-O3", "-march=native", "-ffast-math", "-fPIC", "-shared", "-o", so, src, "-lm"])
+        lib = ctypes.CDLL(so)
+        lib.hnsw_create.restype = ctypes.c_void_p
+        lib.hnsw_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64]
+        lib.hnsw_destroy.argtypes = [ctypes.c_void_p]
+        lib.hnsw_insert.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.hnsw_search.restype = ctypes.c_int
+        lib.hnsw_search.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        _HNSW = lib
+    return _HNSW
+
+
+class HnswIndex:
+    """The reference's default index, restated: HNSW(m=16, ef_construction=64) under cosine, queried
+    with pgvector's default hnsw.ef_search = 40 [external] (init.sql:280-284)."""
+
+    def __init__(self, unit_rows: np.ndarray, m: int = 16, ef_construction: int = 64, seed: int = 1):
+        self.lib = hnsw_lib()
+        self.data = np.ascontiguousarray(unit_rows, dtype=np.float32)
+        n, d = self.data.shape
+        self.h = self.lib.hnsw_create(_ptr(self.data), n, d, m, ef_construction, seed)
+        for i in range(n):
+            self.lib.hnsw_insert(self.h, i)
+
+    def search(self, queries: np.ndarray, k: int, ef_search: int = 40):
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        q = q / np.linalg.norm(q, axis=1, keepdims=True)
+        ids = np.empty((q.shape[0], k), dtype=np.int32)
+        dist = np.empty((q.shape[0], k), dtype=np.float32)
+        for i in range(q.shape[0]):
+            self.lib.hnsw_search(self.h, _ptr(q[i]), k, max(ef_search, 1), _ptr(ids[i]), _ptr(dist[i]))
+        # pgvector returns at most ef_search rows from an index scan [external]
+        if k > ef_search:
+            ids[:, ef_search:] = -1
+        return dist, ids.astype(np.int64)
+
+    def close(self):
+        if self.h:
+            self.lib.hnsw_destroy(self.h)
+            self.h = None
+
+
+def recall_at_k(ids_approx: np.ndarray, ids_exact: np.ndarray) -> float:
+    hits = sum(len(set(a[a >= 0].tolist()) & set(e.tolist())) for a, e in zip(ids_approx, ids_exact))
+    return hits / float(ids_exact.size)

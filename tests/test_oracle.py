@@ -164,3 +164,19 @@ def test_golden_hybrid_and_pool_fixtures(golden_dir):
             assert np.allclose(cc, h[f"{metric}_{ws}_{wb}_combined"], atol=1e-5)
     p = np.load(os.path.join(golden_dir, "pool_6x24x64.npz"))
     assert np.allclose(orc.c_pool_normalize(p["hidden"], p["mask"]), p["pooled"], atol=2e-6)
+
+
+def test_hnsw_restatement_recall_and_truncation():
+    """The reference's default index (HNSW m=16, ef_construction=64, ef_search=40), restated: near-exact
+    on low-intrinsic-dimension rows, and an index scan never returns more than ef_search rows."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((3000, 16)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = rng.standard_normal((40, 16)).astype(np.float32)
+    idx = orc.HnswIndex(x)
+    _, exact = orc.exact_topk("cosine", x, q, 10)
+    _, approx = idx.search(q, 10, ef_search=40)
+    assert orc.recall_at_k(approx, exact) > 0.9
+    _, approx = idx.search(q, 100, ef_search=40)
+    assert (approx[:, 40:] == -1).all() and (approx[:, :40] >= 0).all()
+    idx.close()
