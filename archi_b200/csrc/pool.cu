@@ -54,9 +54,30 @@ __global__ void __launch_bounds__(kPoolThreads) pool_normalize_kernel(const Pool
                                (size_t)b * p.L * p.H * sizeof(HT);
     const size_t mbase = (size_t)b * p.L;
 
-    // sum of the mask
+    // ---- the mask row: weights to shared memory, their sum, and a compact (deterministic, in token
+    //      order) list of the tokens whose weight is not zero -- masked tokens are never read ----
+    float *s_w = spart + (size_t)LS * p.H;               // [L]
+    int *s_live = reinterpret_cast<int *>(s_w + p.L);     // [L]
+    __shared__ int s_wcount[kPoolThreads / 32 + 1];
+    __shared__ int s_nlive;
     float msum = 0.f;
-    for (int t = tid; t < p.L; t += kPoolThreads) msum += mask_at<MT>(p.mask, mbase + t);
+    int base_live = 0;
+    for (int t0 = 0; t0 < p.L; t0 += kPoolThreads) {
+        const int t = t0 + tid;
+        const float w = t < p.L ? mask_at<MT>(p.mask, mbase + t) : 0.f;
+        if (t < p.L) s_w[t] = w;
+        msum += w;
+        const unsigned bal = __ballot_sync(0xffffffffu, w != 0.f);
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_live;
+        for (int wi = 0; wi < warp; ++wi) off += s_wcount[wi];
+        if (w != 0.f) s_live[off + __popc(bal & ((1u << lane) - 1u))] = t;
+        int tot = 0;
+        for (int wi = 0; wi < kPoolThreads / 32; ++wi) tot += s_wcount[wi];
+        base_live += tot;
+        __syncthreads();
+    }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, d);
     if (lane == 0) s_red[warp] = msum;
@@ -65,34 +86,50 @@ __global__ void __launch_bounds__(kPoolThreads) pool_normalize_kernel(const Pool
         float m = 0.f;
         for (int w = 0; w < kPoolThreads / 32; ++w) m += s_red[w];
         s_scalar[0] = fmaxf(m, 1e-9f);
+        s_nlive = base_live;
     }
+    __syncthreads();
+    const int nlive = s_nlive;
 
-    // masked sums: thread (ls, vc) accumulates tokens ls, ls+LS, ... of 16-byte column group vc
+    // masked sums: thread (ls, vc) accumulates live tokens ls, ls+LS, ... of 16-byte column group vc,
+    // eight independent 16-byte loads in flight
     if (ls < LS) {
         for (int vc = vc0; vc < nvec; vc += VT) {
             float acc[VEC];
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-#pragma unroll 4
-            for (int t = ls; t < p.L; t += LS) {
-                const float m = mask_at<MT>(p.mask, mbase + t);
-                if (m != 0.f) {
-                    const uint4 d = *reinterpret_cast<const uint4 *>(
-                        hid + ((size_t)t * p.H + (size_t)vc * VEC) * sizeof(HT));
-                    if constexpr (VEC == 4) {
-                        acc[0] = fmaf(__uint_as_float(d.x), m, acc[0]);
-                        acc[1] = fmaf(__uint_as_float(d.y), m, acc[1]);
-                        acc[2] = fmaf(__uint_as_float(d.z), m, acc[2]);
-                        acc[3] = fmaf(__uint_as_float(d.w), m, acc[3]);
+            const unsigned char *col = hid + (size_t)vc * VEC * sizeof(HT);
+            for (int i0 = ls; i0 < nlive; i0 += 8 * LS) {
+                uint4 d[8];
+                float m[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * LS;
+                    if (i < nlive) {
+                        const int t = s_live[i];
+                        m[u] = s_w[t];
+                        d[u] = *reinterpret_cast<const uint4 *>(col + (size_t)t * p.H * sizeof(HT));
                     } else {
-                        acc[0] = fmaf(__uint_as_float(d.x << 16), m, acc[0]);
-                        acc[1] = fmaf(__uint_as_float(d.x & 0xffff0000u), m, acc[1]);
-                        acc[2] = fmaf(__uint_as_float(d.y << 16), m, acc[2]);
-                        acc[3] = fmaf(__uint_as_float(d.y & 0xffff0000u), m, acc[3]);
-                        acc[4] = fmaf(__uint_as_float(d.z << 16), m, acc[4]);
-                        acc[5] = fmaf(__uint_as_float(d.z & 0xffff0000u), m, acc[5]);
-                        acc[6] = fmaf(__uint_as_float(d.w << 16), m, acc[6]);
-                        acc[7] = fmaf(__uint_as_float(d.w & 0xffff0000u), m, acc[7]);
+                        m[u] = 0.f;
+                        d[u] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if constexpr (VEC == 4) {
+                        acc[0] = fmaf(__uint_as_float(d[u].x), m[u], acc[0]);
+                        acc[1] = fmaf(__uint_as_float(d[u].y), m[u], acc[1]);
+                        acc[2] = fmaf(__uint_as_float(d[u].z), m[u], acc[2]);
+                        acc[3] = fmaf(__uint_as_float(d[u].w), m[u], acc[3]);
+                    } else {
+                        acc[0] = fmaf(__uint_as_float(d[u].x << 16), m[u], acc[0]);
+                        acc[1] = fmaf(__uint_as_float(d[u].x & 0xffff0000u), m[u], acc[1]);
+                        acc[2] = fmaf(__uint_as_float(d[u].y << 16), m[u], acc[2]);
+                        acc[3] = fmaf(__uint_as_float(d[u].y & 0xffff0000u), m[u], acc[3]);
+                        acc[4] = fmaf(__uint_as_float(d[u].z << 16), m[u], acc[4]);
+                        acc[5] = fmaf(__uint_as_float(d[u].z & 0xffff0000u), m[u], acc[5]);
+                        acc[6] = fmaf(__uint_as_float(d[u].w << 16), m[u], acc[6]);
+                        acc[7] = fmaf(__uint_as_float(d[u].w & 0xffff0000u), m[u], acc[7]);
                     }
                 }
             }
@@ -185,8 +222,8 @@ int launch_pool_normalize(const void *hidden, int hidden_dtype, const void *mask
     const int nvec = H / VEC;
     const int VT = nvec < kPoolThreads ? nvec : kPoolThreads;
     const int LS = kPoolThreads / VT;
-    const size_t smem = (size_t)LS * H * sizeof(float);
-    ARCHI_REQUIRE(smem <= 200 * 1024, "pool_normalize: H=%d too large", H);
+    const size_t smem = ((size_t)LS * H + 2 * (size_t)L) * sizeof(float);   // partial sums + mask weights + live list
+    ARCHI_REQUIRE(smem <= 200 * 1024, "pool_normalize: H=%d, L=%d need %zu B of shared memory", H, L, smem);
 
     PoolParams p;
     p.hidden = hidden;

@@ -360,7 +360,9 @@ def main():
         line = {
             "metric": METRIC, "value": batch / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if storage == "f32" else "bf16 storage, f32 accumulate",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": ("f32 (bf16 tensor-core candidate pass over a bf16 shadow, exact fp32 rescoring of every returned row)"
+                      if storage == "f32" else "bf16 storage, fp32 accumulate (exact fp32 rescoring of every returned row)"),
             "data": "synthetic",
             "config": {"workload": desc, "rows": total_rows, "rows_per_gpu": cnt, "dim": dim, "k": k, "batch": batch,
                        "storage": storage, "metric": "cosine", "sharding": f"rows/{world}",
