@@ -555,7 +555,7 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
                 //     index is warp-uniform, so picking the register is a uniform jump, and only the
                 //     lanes that admitted the column store (key, row id) into their own buffer
                 unsigned um = __reduce_or_sync(kFull, mask);
-                if (__popc(um) > 6) {
+                if (__popc(um) > 3) {
                     // dense phase (loose thresholds): 32 predicated stores beat the column walk
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -1239,7 +1239,11 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     int n_phases = 1;
     if (warm && n_ctiles >= 8 * ngroups) {
         bounds[n_phases++] = 2 * ngroups < 32 ? 2 * ngroups : 32;   // <= 32 x 256 keys per query: staged select
-        if (n_ctiles >= 48 * ngroups) bounds[n_phases++] = round_up(n_ctiles / 16, 2 * ngroups);
+        // the main launch wants thresholds drawn from >= ~200 tiles (fewer than ~0.5 admitted columns
+        // per warp and 32-column chunk); a phase change costs ~60 us, so only when the run is long enough
+        int b2 = n_ctiles / 16 > 216 ? n_ctiles / 16 : 216;
+        b2 = round_up(b2, 2 * ngroups);
+        if (n_ctiles >= 4 * b2) bounds[n_phases++] = b2;
     }
     bounds[n_phases] = n_ctiles;
     ThresholdParams tp;
