@@ -80,7 +80,7 @@ def lib() -> ctypes.CDLL:
     L.archi_search.argtypes = [c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_i64, c_p]
     L.archi_hybrid_search.argtypes = [c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_i, c_p, c_p, c_i,
                                       c_i64, c_p]
-    L.archi_bm25_accumulate.argtypes = [c_p, c_i, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p]
+    L.archi_bm25_accumulate.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p]
     L.archi_merge_topk.argtypes = [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
     L.archi_store_last_stats.argtypes = [c_p, ctypes.POINTER(SearchStats)]
     L.archi_store_set_timing.argtypes = [c_p, c_i]

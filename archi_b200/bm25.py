@@ -126,16 +126,14 @@ class LexicalIndex:
         terms = [t for t in self.query_terms(query) if 0 <= t < self._df.size and self._df[t] > 0]
         if not terms or n == 0:
             return out
-        ptr = np.empty(0, dtype=np.int64)
-        # one (start, end) pair per query-term occurrence; the C ABI takes a CSR-style pointer
-        # array, so non-contiguous lists are issued one term at a time
+        # one C-ABI call for all query-term occurrences (posting ranges are arbitrary, not consecutive)
+        starts = np.asarray([self._post_ptr[t] for t in terms], dtype=np.int64)
+        ends = np.asarray([self._post_ptr[t + 1] for t in terms], dtype=np.int64)
+        idf = np.asarray([self.idf(t) for t in terms], dtype=np.float32)
         stream = ctypes.c_void_p(int(torch.cuda.current_stream(self.device).cuda_stream))
-        for t in terms:
-            ptr = np.asarray([self._post_ptr[t], self._post_ptr[t + 1]], dtype=np.int64)
-            idf = np.asarray([self.idf(t)], dtype=np.float32)
-            N.check(N.lib().archi_bm25_accumulate(
-                ptr.ctypes.data_as(ctypes.c_void_p), 1, idf.ctypes.data_as(ctypes.c_void_p),
-                ctypes.c_void_p(self._doc_ids_dev.data_ptr()), ctypes.c_void_p(self._tfs_dev.data_ptr()),
-                ctypes.c_void_p(self._doc_len_dev.data_ptr()), self._avgdl, self.k1, self.b, self.sign,
-                ctypes.c_void_p(out.data_ptr()), stream))
+        N.check(N.lib().archi_bm25_accumulate(
+            starts.ctypes.data_as(ctypes.c_void_p), ends.ctypes.data_as(ctypes.c_void_p), len(terms),
+            idf.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(self._doc_ids_dev.data_ptr()),
+            ctypes.c_void_p(self._tfs_dev.data_ptr()), ctypes.c_void_p(self._doc_len_dev.data_ptr()),
+            self._avgdl, self.k1, self.b, self.sign, ctypes.c_void_p(out.data_ptr()), stream))
         return out

@@ -631,17 +631,18 @@ int archi_hybrid_search(archi_store_t *s, const float *queries, int queries_loc,
                        w_bm25, bm25_dev, out_scores, out_ids, out_loc, id_offset, stream);
 }
 
-int archi_bm25_accumulate(const int64_t *post_ptr_host, int n_terms, const float *idf_host,
-                          const int32_t *doc_ids_dev, const int32_t *tfs_dev, const float *doc_len_dev,
-                          float avgdl, float k1, float b, float sign, float *out_dev, void *stream)
+int archi_bm25_accumulate(const int64_t *post_start_host, const int64_t *post_end_host, int n_terms,
+                          const float *idf_host, const int32_t *doc_ids_dev, const int32_t *tfs_dev,
+                          const float *doc_len_dev, float avgdl, float k1, float b, float sign, float *out_dev,
+                          void *stream)
 {
     ARCHI_REQUIRE(n_terms >= 0, "bm25_accumulate: n_terms < 0");
-    ARCHI_REQUIRE(n_terms == 0 || (post_ptr_host && idf_host && out_dev && doc_len_dev),
+    ARCHI_REQUIRE(n_terms == 0 || (post_start_host && post_end_host && idf_host && out_dev && doc_len_dev),
                   "bm25_accumulate: null argument");
     ARCHI_REQUIRE(avgdl > 0.f, "bm25_accumulate: avgdl must be positive");
     for (int t = 0; t < n_terms; ++t) {
-        const int64_t b0 = post_ptr_host[t], b1 = post_ptr_host[t + 1];
-        ARCHI_REQUIRE(b1 >= b0, "bm25_accumulate: posting pointers must be non-decreasing");
+        const int64_t b0 = post_start_host[t], b1 = post_end_host[t];
+        ARCHI_REQUIRE(b0 >= 0 && b1 >= b0, "bm25_accumulate: bad posting range [%lld, %lld)", (long long)b0, (long long)b1);
         int rc = launch_bm25(doc_ids_dev + b0, tfs_dev + b0, b1 - b0, idf_host[t], doc_len_dev, avgdl, k1, b, sign,
                              out_dev, reinterpret_cast<cudaStream_t>(stream));
         if (rc != ARCHI_OK) return rc;

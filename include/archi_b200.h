@@ -130,11 +130,12 @@ int archi_hybrid_search(archi_store_t *s, const float *queries, int queries_loc,
 
 /* BM25 over device posting lists (replaces pg_textsearch's `chunk_text <@> to_bm25query(...)`,
  * postgres_vectorstore.py:433).  For each query term t (n_terms of them) with postings
- * doc_ids[post_ptr[t] .. post_ptr[t+1]) / tfs[...]:
+ * doc_ids[post_start[t] .. post_end[t]) / tfs[...]:
  *   out[doc] += idf[t] * tf*(k1+1) / (tf + k1*(1 - b + b*doc_len[doc]/avgdl)) * sign
- * out_dev [rows] fp32 must be zeroed by the caller (rows never touched stay 0 = COALESCE). */
-int archi_bm25_accumulate(const int64_t *post_ptr_host, int n_terms, const float *idf_host,
-                          const int32_t *doc_ids_dev, const int32_t *tfs_dev,
+ * Terms are applied in order on `stream` (deterministic sums).  out_dev [rows] fp32 must be zeroed by
+ * the caller (rows never touched stay 0 = COALESCE). */
+int archi_bm25_accumulate(const int64_t *post_start_host, const int64_t *post_end_host, int n_terms,
+                          const float *idf_host, const int32_t *doc_ids_dev, const int32_t *tfs_dev,
                           const float *doc_len_dev, float avgdl, float k1, float b, float sign,
                           float *out_dev, void *stream);
 
