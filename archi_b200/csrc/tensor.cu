@@ -214,6 +214,9 @@ struct CoarseParams {
     int trigger;          // a buffer holding at least this many entries is compacted after the tile
     int tile_begin, tile_end;  // corpus tiles [tile_begin, tile_end) are scanned by this launch
     int resume;           // 1: continue from the candidate counts / thresholds left by a previous launch
+    int maxima_only;      // 1: probe launch -- record the maximum live key of every 32-column chunk, store nothing
+    float *chunkmax;      // [grid * 2][cm_slots][BM] chunk maxima of a probe launch
+    int cm_slots;         // maxima kept per (CTA, group, query)
     int debug;            // profiling aid (ARCHI_TC_DEBUG): 1 = skip the MMAs, 2 = skip the epilogue math
     int exit_cap;         // buffers larger than this are compacted before the CTA exits
     const float2 *aux;    // [n] (a, b) per row -- aux mode only
@@ -491,6 +494,10 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
             }
             cnt = w;
         }
+        float *cmx = p.chunkmax + vcta * p.cm_slots * BM + tq;     // [slot][query]: coalesced per warp
+        int mslot = 0;
+        if (p.maxima_only && active)
+            for (int i = 0; i < p.cm_slots; ++i) cmx[i * BM] = -CUDART_INF_F;
         int u = grp;
         for (int ct = p.tile_begin + group + grp * p.ngroups; ct < p.tile_end; ct += 2 * p.ngroups, u += 2) {
             const uint32_t aph = (uint32_t)(u >> 1) & 1u;
@@ -527,6 +534,27 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
             //      (compaction trigger), so a tile cannot overflow the buffer.
             auto process = [&](uint32_t (&r)[32], int c) {
                 uint32_t mask = 0u;
+                if (p.maxima_only) {
+                    // probe launch: the largest key among the live columns of this chunk; the k'-th
+                    // largest chunk maximum of a query bounds its final k'-th best key from below
+                    // (chunk maxima belong to distinct rows)
+                    float mx = -CUDART_INF_F;
+                    if (RAW) {
+                        const uint32_t live = __shfl_sync(kFull, tile_word, c);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            mx = fmaxf(mx, ((live >> j) & 1u) ? __uint_as_float(r[j]) : -CUDART_INF_F);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float2 ab = aux_w[c * 32 + j];
+                            mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), ab.x, ab.y));
+                        }
+                    }
+                    if (active && mslot < p.cm_slots) cmx[mslot * BM] = mx;
+                    ++mslot;
+                    return;
+                }
                 if (RAW) {
                     // chunk maximum first: most chunks of the main phase beat no lane's threshold
                     float m[11];
@@ -653,7 +681,7 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
             }
         }
         // exit: bound the number of candidates the select kernel has to look at
-        unsigned need = __ballot_sync(kFull, cnt > p.exit_cap);
+        unsigned need = __ballot_sync(kFull, !p.maxima_only && cnt > p.exit_cap);
         while (need) {
             const int owner = __ffs(need) - 1;
             need &= need - 1;
@@ -859,6 +887,42 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const Thresho
     int total;
     const uint32_t T = sel_radix_threshold(p.c, blockIdx.x, s_cnt, s_hist, s_misc, s_stage, total);
     if (threadIdx.x == 0 && total > p.c.kprime) atomicMax(p.thr_g + blockIdx.x, T);
+}
+
+// After a probe launch: per query, the kprime-th largest chunk maximum over all lists becomes the
+// shared threshold (chunk maxima are keys of distinct rows, so at least kprime rows reach it).
+struct MaxThrParams {
+    const float *chunkmax;
+    int qt_count, ngroups, cm_slots, kprime;
+    uint32_t *thr_g;
+};
+
+__global__ void __launch_bounds__(SEL_THREADS) tc_maxima_threshold_kernel(const MaxThrParams p)
+{
+    extern __shared__ uint32_t s_mkeys[];            // [2 * ngroups * cm_slots]
+    __shared__ int s_hist[256 * (SEL_THREADS / 32)];
+    __shared__ int s_misc[8];
+    __shared__ int s_valid;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int qt = q / BM, tq = q % BM;
+    const int total = 2 * p.ngroups * p.cm_slots;
+    if (tid == 0) s_valid = 0;
+    __syncthreads();
+    int valid = 0;
+    for (int i = tid; i < total; i += SEL_THREADS) {
+        const int l = i / p.cm_slots, sl = i - l * p.cm_slots;
+        const size_t vcta = ((size_t)((l >> 1) * p.qt_count + qt)) * 2 + (l & 1);
+        const float v = p.chunkmax[(vcta * p.cm_slots + sl) * BM + tq];
+        s_mkeys[i] = fmap(v);
+        valid += v > -CUDART_INF_F ? 1 : 0;
+    }
+    valid = __reduce_add_sync(kFull, valid);
+    if (lane == 0 && valid) atomicAdd(&s_valid, valid);
+    __syncthreads();
+    if (s_valid < p.kprime) return;                  // fewer live rows than kprime seen: no threshold yet
+    int n_gt;
+    const uint32_t T = block_radix_kth(s_mkeys, total, p.kprime, s_hist, s_misc, n_gt);
+    if (tid == 0) atomicMax(p.thr_g + q, T);
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
@@ -1235,15 +1299,62 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     // the corpus then runs with thresholds ~2*ngroups times tighter than local ones and its epilogue
     // almost never stores.  ARCHI_TC_WARM=0 disables the scheme.
     static const int warm = getenv("ARCHI_TC_WARM") ? atoi(getenv("ARCHI_TC_WARM")) : 1;
+    // warm == 1 (default): PROBE scheme.  A first launch scans a small prefix of the corpus (about
+    // 1/12, at most 8 tiles per epilogue group) and only records the maximum live key of every
+    // 32-column chunk; tc_maxima_threshold_kernel turns the kprime-th largest chunk maximum of each
+    // query into its shared threshold; one main launch then scans everything.  No flood of
+    // candidates, no resume.  warm == 2: the older flood + resume phases (kept for comparison);
+    // warm == 0: no warm-up at all.
+    bool probed = false;
+    if (warm == 1 && n_ctiles >= 8 * ngroups) {
+        const int nlists = 2 * ngroups;
+        int cm_slots = (8192 / nlists) / 8 * 8;
+        if (cm_slots > 64) cm_slots = 64;
+        if (cm_slots < 8) cm_slots = 8;
+        int per_vcta = (n_ctiles / 12) / nlists;
+        if (per_vcta > cm_slots / 8) per_vcta = cm_slots / 8;
+        if (per_vcta < 1) per_vcta = 1;
+        if ((rc = ensure_buf(&w.chunkmax, &w.chunkmax_bytes, (size_t)grid * 2 * BM * cm_slots * sizeof(float))) != ARCHI_OK)
+            return rc;
+        if (s->timing) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
+        cp.tile_begin = 0;
+        cp.tile_end = per_vcta * nlists;
+        cp.resume = 0;
+        cp.maxima_only = 1;
+        cp.chunkmax = w.chunkmax;
+        cp.cm_slots = cm_slots;
+        kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmap_q, tmap_c, cp);
+        ARCHI_CHECK_LAUNCH();
+        MaxThrParams mp;
+        mp.chunkmax = w.chunkmax;
+        mp.qt_count = qt_count;
+        mp.ngroups = ngroups;
+        mp.cm_slots = cm_slots;
+        mp.kprime = kprime;
+        mp.thr_g = w.thr_g;
+        tc_maxima_threshold_kernel<<<nq, SEL_THREADS, (size_t)nlists * cm_slots * 4, st>>>(mp);
+        ARCHI_CHECK_LAUNCH();
+        probed = true;
+    }
+    cp.maxima_only = 0;
+    cp.chunkmax = w.chunkmax;
+    cp.cm_slots = 8;
     int bounds[4] = {0, 0, 0, 0};
     int n_phases = 1;
-    if (warm && n_ctiles >= 8 * ngroups) {
+    if (warm == 2 && n_ctiles >= 8 * ngroups) {
         bounds[n_phases++] = 2 * ngroups < 32 ? 2 * ngroups : 32;   // <= 32 x 256 keys per query: staged select
         // the main launch wants thresholds drawn from >= ~200 tiles (fewer than ~0.5 admitted columns
         // per warp and 32-column chunk); a phase change costs ~60 us, so only when the run is long enough
         int b2 = n_ctiles / 16 > 216 ? n_ctiles / 16 : 216;
         b2 = round_up(b2, 2 * ngroups);
         if (n_ctiles >= 4 * b2) bounds[n_phases++] = b2;
+    }
+    if (probed) {
+        // Long scans: the probe's threshold (k' of ~probe rows) stays loose for the whole main launch
+        // unless buffers fill.  Tighten it once from the candidates of the first 1/16 of the corpus.
+        static const int p2div = getenv("ARCHI_TC_P2") ? atoi(getenv("ARCHI_TC_P2")) : 16;
+        const int probe_tiles = cp.tile_end;
+        if (p2div > 0 && n_ctiles / p2div >= 3 * probe_tiles) bounds[n_phases++] = round_up(n_ctiles / p2div, 2 * ngroups);
     }
     bounds[n_phases] = n_ctiles;
     ThresholdParams tp;
@@ -1254,7 +1365,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     tp.c.cap = cap;
     tp.c.kprime = kprime;
     tp.thr_g = w.thr_g;
-    if (s->timing) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
+    if (s->timing && !probed) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
     for (int ph = 0; ph < n_phases; ++ph) {
         cp.tile_begin = bounds[ph];
         cp.tile_end = bounds[ph + 1];
@@ -1310,13 +1421,13 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         ARCHI_CUDA(cudaMemcpy(unverified_host, w.unverified, (size_t)nq * 4, cudaMemcpyDeviceToHost));
     s->stats.grid = grid;
     s->stats.coarse_dtype = tf32 ? ARCHI_F32 : ARCHI_BF16;
-    s->stats.coarse_launches = n_phases;
+    s->stats.coarse_launches = n_phases + (probed ? 1 : 0);
     return ARCHI_OK;
 }
 
 void free_tensor_workspace(TensorWorkspace &w)
 {
-    void *ptrs[] = {w.qstage, w.qinfo, w.thr_g, w.unverified, w.cand, w.cand_cnt, w.aux, w.max_norm2, w.shadow};
+    void *ptrs[] = {w.qstage, w.qinfo, w.thr_g, w.unverified, w.cand, w.cand_cnt, w.aux, w.max_norm2, w.shadow, w.chunkmax};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     w = TensorWorkspace();
