@@ -214,6 +214,7 @@ struct CoarseParams {
     int trigger;          // a buffer holding at least this many entries is compacted after the tile
     int tile_begin, tile_end;  // corpus tiles [tile_begin, tile_end) are scanned by this launch
     int resume;           // 1: continue from the candidate counts / thresholds left by a previous launch
+    int split;            // 1: both epilogue groups drain every tile, half the columns each
     int maxima_only;      // 1: probe launch -- record the maximum live key of every 32-column chunk, store nothing
     float *chunkmax;      // [grid * 2][cm_slots][BM] chunk maxima of a probe launch
     int cm_slots;         // maxima kept per (CTA, group, query)
@@ -366,7 +367,8 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull_bar + 8 * a, 1);
-            ptx::mbar_init(tempty_bar + 8 * a, TWO ? 8 : 4);   // pair mode: both CTAs' epilogues release the leader
+            // one arrival per epilogue warp that drains the buffer (pair mode: both CTAs' warps release the leader)
+            ptx::mbar_init(tempty_bar + 8 * a, (TWO ? 8 : 4) * (p.split ? 2 : 1));
         }
         ptx::fence_barrier_init();
     }
@@ -498,9 +500,15 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
         int mslot = 0;
         if (p.maxima_only && active)
             for (int i = 0; i < p.cm_slots; ++i) cmx[i * BM] = -CUDART_INF_F;
-        int u = grp;
-        for (int ct = p.tile_begin + group + grp * p.ngroups; ct < p.tile_end; ct += 2 * p.ngroups, u += 2) {
+        // split == 0: group g drains accumulator g (tiles u = g, g+2, ...), all 8 chunks of the tile.
+        // split == 1: both groups drain every tile, group g taking chunks 4g .. 4g+3, so a buffer is
+        //             handed back after half an epilogue and the MMA warp tolerates T_epi <= 2 T_mma.
+        const int ustep = p.split ? 1 : 2;
+        const int c_begin = p.split ? grp * (BN / 64) : 0, c_end = p.split ? c_begin + BN / 64 : BN / 32;
+        int u = p.split ? 0 : grp;
+        for (int ct = p.tile_begin + group + u * p.ngroups; ct < p.tile_end; ct += ustep * p.ngroups, u += ustep) {
             const uint32_t aph = (uint32_t)(u >> 1) & 1u;
+            const int acc = u & 1;
             // this tile's per-row constants, fetched while the MMAs run (warp-private: no CTA barrier)
             uint32_t tile_word = 0u;                 // raw mode: lane j < 8 holds the live-row bits of chunk j
             if (RAW) {
@@ -523,9 +531,9 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
             if (active) thr = fmaxf(thr, thr_from_word(__ldcg(p.thr_g + q)));
             __syncwarp();
 
-            ptx::mbar_wait(tfull_bar + 8 * grp, aph);
+            ptx::mbar_wait(tfull_bar + 8 * acc, aph);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
             const uint32_t row_base = (uint32_t)ct * BN;
 
             // One 32-column chunk in two passes so that the loads / FMAs of all columns overlap:
@@ -645,22 +653,22 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
                 }
             };
             uint32_t ra[32], rb[32];
-            ptx::tmem_ld_32x32(taddr, ra);
+            ptx::tmem_ld_32x32(taddr + c_begin * 32, ra);
 #pragma unroll 1
-            for (int c = 0; c < ((p.debug & 2) ? 0 : BN / 32); c += 2) {
+            for (int c = c_begin; c < ((p.debug & 2) ? 0 : c_end); c += 2) {
                 ptx::tmem_ld_wait();
                 ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);      // next chunk in flight
                 process(ra, c);
                 ptx::tmem_ld_wait();
-                if (c + 2 < BN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+                if (c + 2 < c_end) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
                 process(rb, c + 1);
             }
             // accumulator drained: hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (TWO) ptx::mbar_arrive_cluster(tempty_bar_leader + 8 * grp);
-                else ptx::mbar_arrive(tempty_bar + 8 * grp);
+                if (TWO) ptx::mbar_arrive_cluster(tempty_bar_leader + 8 * acc);
+                else ptx::mbar_arrive(tempty_bar + 8 * acc);
             }
 
             // eager compaction keeps the thresholds tight (warp-collective, one owner lane at a time)
@@ -1277,6 +1285,9 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     {
         const char *dbg = getenv("ARCHI_TC_DEBUG");
         cp.debug = dbg ? atoi(dbg) : 0;
+        // column-split epilogue: pays when a tile's MMAs are short (measured: D=384 step -8 %, D>=768 +-2 %)
+        static const int split = getenv("ARCHI_TC_SPLIT") ? atoi(getenv("ARCHI_TC_SPLIT")) : -1;
+        cp.split = split >= 0 ? split : (cp.kchunks * (tf32 ? 2 : 1) <= 8 ? 1 : 0);
     }
     cp.exit_cap = cap;           // final launch: nothing to bound (the select kernel walks global memory)
     cp.aux = reinterpret_cast<const float2 *>(w.aux);
@@ -1311,7 +1322,8 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         int cm_slots = (8192 / nlists) / 8 * 8;
         if (cm_slots > 64) cm_slots = 64;
         if (cm_slots < 8) cm_slots = 8;
-        int per_vcta = (n_ctiles / 12) / nlists;
+        static const int probe_div = getenv("ARCHI_TC_PROBE") ? atoi(getenv("ARCHI_TC_PROBE")) : 12;
+        int per_vcta = (n_ctiles / probe_div) / nlists;
         if (per_vcta > cm_slots / 8) per_vcta = cm_slots / 8;
         if (per_vcta < 1) per_vcta = 1;
         if ((rc = ensure_buf(&w.chunkmax, &w.chunkmax_bytes, (size_t)grid * 2 * BM * cm_slots * sizeof(float))) != ARCHI_OK)

@@ -282,7 +282,8 @@ def main():
         t_tc = algo_flops / (peaks["bf16_tflops"] * 1e12)
         kname = "tc_coarse_kernel<bf16>" if st.coarse_dtype == N.BF16 else "tc_coarse_kernel<tf32>"
         if st.coarse_launches > 1:
-            kname += f" x{st.coarse_launches} (warm-up phases + main) + tc_threshold_kernel x{st.coarse_launches - 1}, timed together"
+            kname += (f" x{st.coarse_launches} (probe launch over ~1/12 of the rows + main scan) + threshold kernel "
+                      f"x{st.coarse_launches - 1}, timed together; the probe's flops/bytes are NOT counted as algorithmic work")
         common = {"traffic": profiled_traffic("tc_coarse_kernel", args.workload, nq_all) if world == 1 else None,
                   "kernel": kname, "coarse_reads": "bf16 shadow of the fp32 rows" if (storage == "f32" and st.coarse_dtype == N.BF16) else storage + " rows",
                   "launch_ms": launch_ms, "algorithmic_bytes_per_launch": algo_bytes,
