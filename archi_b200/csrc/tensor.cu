@@ -73,6 +73,7 @@ struct PrepParams {
     QInfo *qinfo;          // [nq]
     uint32_t *thr_g;       // [nq] shared thresholds (mapped), reset to 0
     int *unverified;       // [nq]
+    int *n_unverified;     // counter of unverified queries, reset here
     const float *max_norm2;// [1] max |row|^2 over the store
     float corpus_rel_err;  // 2^-9 when the coarse pass reads a bf16 shadow of fp32 rows, else 0
     int cos_raw_unnorm;    // cosine scored as a raw dot over rows that are only approximately unit length
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(const PrepParams p)
         p.qinfo[q] = qi;
         p.thr_g[q] = 0u;
         p.unverified[q] = 0;
+        if (q == 0) *p.n_unverified = 0;
     }
 }
 
@@ -505,6 +507,7 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
         //             handed back after half an epilogue and the MMA warp tolerates T_epi <= 2 T_mma.
         const int ustep = p.split ? 1 : 2;
         const int c_begin = p.split ? grp * (BN / 64) : 0, c_end = p.split ? c_begin + BN / 64 : BN / 32;
+        uint32_t thr_word = active ? __ldcg(p.thr_g + q) : 0u;
         int u = p.split ? 0 : grp;
         for (int ct = p.tile_begin + group + u * p.ngroups; ct < p.tile_end; ct += ustep * p.ngroups, u += ustep) {
             const uint32_t aph = (uint32_t)(u >> 1) & 1u;
@@ -528,7 +531,12 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
                     aux_w[i * 32 + lane] = r < p.n ? __ldg(p.aux + r) : make_float2(0.f, -CUDART_INF_F);
                 }
             }
-            if (active) thr = fmaxf(thr, thr_from_word(__ldcg(p.thr_g + q)));
+            // shared threshold: use the word fetched during the previous tile and fetch the next one
+            // now, so that the L2 round trip never sits between "accumulator full" and the first compare
+            if (active) {
+                thr = fmaxf(thr, thr_from_word(thr_word));
+                thr_word = __ldcg(p.thr_g + q);
+            }
             __syncwarp();
 
             ptx::mbar_wait(tfull_bar + 8 * acc, aph);
@@ -781,43 +789,64 @@ __device__ __forceinline__ size_t sel_list_base(const SelCommon &c, int l, int q
 
 constexpr int SEL_STAGE = 8192;   // keys staged in shared memory for the radix passes when they fit
 
-// s_cnt[320], s_hist[256], s_misc[4], s_stage[SEL_STAGE] are shared-memory scratch; returns T, total via total_out
-__device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int q, int *s_cnt, int *s_hist, int *s_misc,
-                                                       uint32_t *s_stage, int &total_out)
+constexpr int SEL_LISTS_MAX = 320;   // 2 * ngroups <= 296
+
+// Candidate `i` of the query's concatenated lists (s_off = exclusive prefix sums of the list sizes,
+// s_off[nlists] = total): which list, and where inside it.
+__device__ __forceinline__ const uint2 *sel_locate(const SelCommon &c, const int *s_off, int nlists, int qt, int tq, int i)
+{
+    int lo = 0, hi = nlists;               // largest l with s_off[l] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    return c.cand + (sel_list_base(c, lo, qt) * BM + tq) * c.cap + (i - s_off[lo]);
+}
+
+// s_cnt[SEL_LISTS_MAX], s_off[SEL_LISTS_MAX + 1], s_hist[256 * warps], s_misc[8], s_stage[SEL_STAGE] are
+// shared-memory scratch; returns T, the number of candidates through total_out.  When total <= SEL_STAGE
+// the mapped keys are left in s_stage in concatenated-list order (see sel_locate).
+__device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int q, int *s_cnt, int *s_off, int *s_hist,
+                                                       int *s_misc, uint32_t *s_stage, int &total_out)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qt = q / BM, tq = q % BM;
     const int nlists = 2 * c.ngroups;
-    if (tid == 0) s_misc[0] = 0;
+    for (int l = tid; l < nlists; l += SEL_THREADS) s_cnt[l] = c.cand_cnt[sel_list_base(c, l, qt) * BM + tq];
     __syncthreads();
-    int part = 0;
-    for (int l = tid; l < nlists; l += SEL_THREADS) {
-        const int n = c.cand_cnt[sel_list_base(c, l, qt) * BM + tq];
-        s_cnt[l] = n;
-        part += n;
+    if (warp == 0) {
+        // exclusive prefix sums: lane L owns lists [10 L, 10 L + 10)
+        int mine = 0;
+        for (int j = 0; j < SEL_LISTS_MAX / 32; ++j) {
+            const int l = lane * (SEL_LISTS_MAX / 32) + j;
+            mine += l < nlists ? s_cnt[l] : 0;
+        }
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += o;
+        }
+        int run = incl - mine;
+        for (int j = 0; j < SEL_LISTS_MAX / 32; ++j) {
+            const int l = lane * (SEL_LISTS_MAX / 32) + j;
+            if (l < nlists) {
+                s_off[l] = run;
+                run += s_cnt[l];
+            }
+        }
+        if (lane == 31) s_off[nlists] = incl;
     }
-    part = __reduce_add_sync(kFull, part);
-    if (lane == 0 && part) atomicAdd(&s_misc[0], part);
     __syncthreads();
-    const int total = s_misc[0];
+    const int total = s_off[nlists];
     total_out = total;
     if (total <= c.kprime) return 0u;
     const bool staged = total <= SEL_STAGE;
     if (staged) {
-        // one walk over global memory; slots are claimed per list chunk (order is irrelevant)
-        if (tid == 0) s_misc[3] = 0;
-        __syncthreads();
-        for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
-            const int n = s_cnt[l];
-            const uint2 *src = c.cand + (sel_list_base(c, l, qt) * BM + tq) * c.cap;
-            for (int i0 = 0; i0 < n; i0 += 32) {
-                const int m = n - i0 < 32 ? n - i0 : 32;
-                int slot = 0;
-                if (lane == 0) slot = atomicAdd(&s_misc[3], m);
-                slot = __shfl_sync(kFull, slot, 0);
-                if (lane < m) s_stage[slot + lane] = fmap(__uint_as_float(src[i0 + lane].x));
-            }
-        }
+        // one walk over global memory, every load independent of the others (this kernel is latency bound)
+        for (int i = tid; i < total; i += SEL_THREADS)
+            s_stage[i] = fmap(__uint_as_float(__ldcg(&sel_locate(c, s_off, nlists, qt, tq, i)->x)));
         __syncthreads();
         int n_gt;
         return block_radix_kth(s_stage, total, c.kprime, s_hist, s_misc, n_gt);
@@ -888,12 +917,13 @@ struct ThresholdParams {
 
 __global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const ThresholdParams p)
 {
-    __shared__ int s_cnt[320];
+    __shared__ int s_cnt[SEL_LISTS_MAX];
+    __shared__ int s_off[SEL_LISTS_MAX + 1];
     __shared__ int s_hist[256 * (SEL_THREADS / 32)];
     __shared__ int s_misc[8];
     __shared__ uint32_t s_stage[SEL_STAGE];
     int total;
-    const uint32_t T = sel_radix_threshold(p.c, blockIdx.x, s_cnt, s_hist, s_misc, s_stage, total);
+    const uint32_t T = sel_radix_threshold(p.c, blockIdx.x, s_cnt, s_off, s_hist, s_misc, s_stage, total);
     if (threadIdx.x == 0 && total > p.c.kprime) atomicMax(p.thr_g + blockIdx.x, T);
 }
 
@@ -901,49 +931,68 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const Thresho
 // shared threshold (chunk maxima are keys of distinct rows, so at least kprime rows reach it).
 struct MaxThrParams {
     const float *chunkmax;
-    int qt_count, ngroups, cm_slots, kprime;
+    int qt_count, ngroups, cm_slots, used_slots, kprime, nq;
     uint32_t *thr_g;
 };
 
-__global__ void __launch_bounds__(SEL_THREADS) tc_maxima_threshold_kernel(const MaxThrParams p)
+constexpr int MAXTHR_Q = 8;            // queries per CTA of tc_maxima_threshold_kernel: one warp each for the selection
+constexpr int MAXTHR_THREADS = 1024;   // ... after all 32 warps gathered the maxima (latency bound: wide is fast)
+
+__global__ void __launch_bounds__(MAXTHR_THREADS) tc_maxima_threshold_kernel(const MaxThrParams p)
 {
-    extern __shared__ uint32_t s_mkeys[];            // [2 * ngroups * cm_slots]
-    __shared__ int s_hist[256 * (SEL_THREADS / 32)];
-    __shared__ int s_misc[8];
-    __shared__ int s_valid;
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const int qt = q / BM, tq = q % BM;
-    const int total = 2 * p.ngroups * p.cm_slots;
-    if (tid == 0) s_valid = 0;
-    __syncthreads();
-    int valid = 0;
-    for (int i = tid; i < total; i += SEL_THREADS) {
-        const int l = i / p.cm_slots, sl = i - l * p.cm_slots;
-        const size_t vcta = ((size_t)((l >> 1) * p.qt_count + qt)) * 2 + (l & 1);
-        const float v = p.chunkmax[(vcta * p.cm_slots + sl) * BM + tq];
-        s_mkeys[i] = fmap(v);
-        valid += v > -CUDART_INF_F ? 1 : 0;
+    extern __shared__ uint32_t s_mkeys[];            // [MAXTHR_Q][stride >= 2 * ngroups * used_slots]
+    __shared__ int s_hist[MAXTHR_Q][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q0 = blockIdx.x * MAXTHR_Q;            // MAXTHR_Q divides BM: all in one query tile
+    const int qt = q0 / BM, tq0 = q0 % BM;
+    const int total = 2 * p.ngroups * p.used_slots;
+    const int stride = ((total + 31) & ~31) + 4;     // bank-conflict-free transposed stores
+    // gather: 8 consecutive queries of one (list, slot) are one 32-byte sector; 8 loads in flight per thread
+    const int j = tid % MAXTHR_Q, n_el = total * MAXTHR_Q;
+    for (int base = tid; base < n_el; base += MAXTHR_THREADS * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * MAXTHR_THREADS;
+            if (i < n_el) {
+                const int e = i / MAXTHR_Q;
+                const int l = e / p.used_slots, sl = e - l * p.used_slots;
+                const size_t vcta = ((size_t)((l >> 1) * p.qt_count + qt)) * 2 + (l & 1);
+                v[u] = __ldcg(p.chunkmax + (vcta * p.cm_slots + sl) * BM + tq0 + j);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * MAXTHR_THREADS;
+            if (i < n_el) s_mkeys[j * stride + i / MAXTHR_Q] = fmap(v[u]);
+        }
     }
-    valid = __reduce_add_sync(kFull, valid);
-    if (lane == 0 && valid) atomicAdd(&s_valid, valid);
     __syncthreads();
-    if (s_valid < p.kprime) return;                  // fewer live rows than kprime seen: no threshold yet
-    int n_gt;
-    const uint32_t T = block_radix_kth(s_mkeys, total, p.kprime, s_hist, s_misc, n_gt);
-    if (tid == 0) atomicMax(p.thr_g + q, T);
+    const int q = q0 + warp;
+    if (warp >= MAXTHR_Q || q >= p.nq) return;
+    const uint32_t *keys = s_mkeys + warp * stride;
+    const uint32_t none = fmap(-CUDART_INF_F);
+    int valid = 0;
+#pragma unroll 8
+    for (int i = lane; i < total; i += 32) valid += keys[i] > none ? 1 : 0;
+    valid = __reduce_add_sync(kFull, valid);
+    if (valid < p.kprime) return;                    // fewer live rows than kprime seen: no threshold yet
+    const uint32_t T = warp_radix_kth(keys, total, p.kprime, s_hist[warp], lane);
+    if (lane == 0) atomicMax(p.thr_g + q, T);
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
 {
-    __shared__ int s_cnt[320];                      // per-list sizes (2 * ngroups <= 296)
+    __shared__ int s_cnt[SEL_LISTS_MAX];            // per-list sizes and their exclusive prefix sums
+    __shared__ int s_off[SEL_LISTS_MAX + 1];
     __shared__ int s_hist[256 * (SEL_THREADS / 32)];
     __shared__ int s_misc[8];
     __shared__ uint32_t s_stage[SEL_STAGE];
     __shared__ int s_nk;
     __shared__ uint32_t s_kid[KEPT_MAX];
-    __shared__ float s_kc[KEPT_MAX];                // coarse key of the kept candidates
     __shared__ float s_ex[KEPT_MAX];                // exact key (coarse-key space)
     __shared__ float s_sc[KEPT_MAX];                // output score
+    extern __shared__ __align__(16) float s_q[];    // [ld] the query, zero padded to the row stride
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qt = q / BM, tq = q % BM;
     const int nlists = 2 * p.ngroups;
@@ -955,21 +1004,31 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     sc.cap = p.cap;
     sc.kprime = p.kprime;
     if (tid == 0) s_nk = 0;
+    // the query is needed last: fetch it first, its latency hides behind the selection
+    for (int e = tid; e < p.ld; e += SEL_THREADS) s_q[e] = e < p.dim ? p.queries[(size_t)q * p.dim + e] : 0.f;
+    const QInfo qi = p.qinfo[q];
     int total;
-    const uint32_t T = sel_radix_threshold(sc, q, s_cnt, s_hist, s_misc, s_stage, total);
+    const uint32_t T = sel_radix_threshold(sc, q, s_cnt, s_off, s_hist, s_misc, s_stage, total);
     __syncthreads();
 
     // gather the survivors (key >= T)
-    for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
-        const int n = s_cnt[l];
-        const uint2 *src = p.cand + (sel_list_base(sc, l, qt) * BM + tq) * p.cap;
-        for (int i = lane; i < n; i += 32) {
-            const uint2 e = src[i];
-            if (fmap(__uint_as_float(e.x)) >= T) {
+    if (total <= SEL_STAGE) {
+        // keys are staged in list order: only the survivors' row ids come from global memory
+        for (int i = tid; i < total; i += SEL_THREADS) {
+            if (total <= p.kprime || s_stage[i] >= T) {
                 const int slot = atomicAdd(&s_nk, 1);
-                if (slot < KEPT_MAX) {
-                    s_kid[slot] = e.y;
-                    s_kc[slot] = __uint_as_float(e.x);
+                if (slot < KEPT_MAX) s_kid[slot] = __ldcg(&sel_locate(sc, s_off, nlists, qt, tq, i)->y);
+            }
+        }
+    } else {
+        for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
+            const int n = s_cnt[l];
+            const uint2 *src = p.cand + (sel_list_base(sc, l, qt) * BM + tq) * p.cap;
+            for (int i = lane; i < n; i += 32) {
+                const uint2 e = src[i];
+                if (fmap(__uint_as_float(e.x)) >= T) {
+                    const int slot = atomicAdd(&s_nk, 1);
+                    if (slot < KEPT_MAX) s_kid[slot] = e.y;
                 }
             }
         }
@@ -978,63 +1037,76 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     const bool overflow = s_nk > KEPT_MAX;          // more ties at T than we can hold: cannot prove
     const int nk = overflow ? KEPT_MAX : s_nk;
 
-    // exact fp32 rescoring, one warp per candidate: the query sits in shared memory (zero padded to
-    // the row stride), the stored row is read with 16-byte loads
-    extern __shared__ __align__(16) float s_q[];      // [ld]
-    const QInfo qi = p.qinfo[q];
-    for (int e = tid; e < p.ld; e += SEL_THREADS) s_q[e] = e < p.dim ? p.queries[(size_t)q * p.dim + e] : 0.f;
-    __syncthreads();
+    // exact fp32 rescoring: a warp takes four candidates at a time and keeps the loads of all four
+    // rows (16-byte loads) and their norms in flight together
     const int vec = p.dtype == ARCHI_BF16 ? 8 : 4;
     const int nvec = p.ld / vec;
-    for (int c = warp; c < nk; c += SEL_THREADS / 32) {
-        const size_t row = s_kid[c];
-        const uint4 *rp = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(p.corpus) +
-                                                          row * p.ld * (p.dtype == ARCHI_BF16 ? 2 : 4));
-        float acc = 0.f;
+    const size_t row_bytes = (size_t)p.ld * (p.dtype == ARCHI_BF16 ? 2 : 4);
+    for (int cb = warp * 4; cb < nk; cb += (SEL_THREADS / 32) * 4) {
+        size_t row[4];
+        const uint4 *rp[4];
+        float n2[4], acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            row[j] = s_kid[cb + j < nk ? cb + j : cb];
+            rp[j] = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(p.corpus) + row[j] * row_bytes);
+            n2[j] = p.metric == ARCHI_COSINE ? __ldg(p.norm2 + row[j]) : 1.f;
+            acc[j] = 0.f;
+        }
         for (int v = lane; v < nvec; v += 32) {
-            const uint4 d = __ldg(rp + v);
-            float x[8];
-            if (p.dtype == ARCHI_BF16) {
-                x[0] = __uint_as_float(d.x << 16); x[1] = __uint_as_float(d.x & 0xffff0000u);
-                x[2] = __uint_as_float(d.y << 16); x[3] = __uint_as_float(d.y & 0xffff0000u);
-                x[4] = __uint_as_float(d.z << 16); x[5] = __uint_as_float(d.z & 0xffff0000u);
-                x[6] = __uint_as_float(d.w << 16); x[7] = __uint_as_float(d.w & 0xffff0000u);
-            } else {
-                x[0] = __uint_as_float(d.x); x[1] = __uint_as_float(d.y);
-                x[2] = __uint_as_float(d.z); x[3] = __uint_as_float(d.w);
-                x[4] = x[5] = x[6] = x[7] = 0.f;
-            }
+            uint4 d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = __ldg(rp[j] + v);
             const float *qq = s_q + v * vec;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i < vec) {
-                    if (p.metric == ARCHI_L2) {
-                        const float t = x[i] - qq[i];
-                        acc = fmaf(t, t, acc);
-                    } else {
-                        acc = fmaf(x[i], qq[i], acc);
+            for (int j = 0; j < 4; ++j) {
+                float x[8];
+                if (p.dtype == ARCHI_BF16) {
+                    x[0] = __uint_as_float(d[j].x << 16); x[1] = __uint_as_float(d[j].x & 0xffff0000u);
+                    x[2] = __uint_as_float(d[j].y << 16); x[3] = __uint_as_float(d[j].y & 0xffff0000u);
+                    x[4] = __uint_as_float(d[j].z << 16); x[5] = __uint_as_float(d[j].z & 0xffff0000u);
+                    x[6] = __uint_as_float(d[j].w << 16); x[7] = __uint_as_float(d[j].w & 0xffff0000u);
+                } else {
+                    x[0] = __uint_as_float(d[j].x); x[1] = __uint_as_float(d[j].y);
+                    x[2] = __uint_as_float(d[j].z); x[3] = __uint_as_float(d[j].w);
+                    x[4] = x[5] = x[6] = x[7] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < vec) {
+                        if (p.metric == ARCHI_L2) {
+                            const float t = x[i] - qq[i];
+                            acc[j] = fmaf(t, t, acc[j]);
+                        } else {
+                            acc[j] = fmaf(x[i], qq[i], acc[j]);
+                        }
                     }
                 }
             }
         }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
-        if (lane == 0) {
-            float ex, sc;
-            if (p.metric == ARCHI_COSINE) {
-                const float n2 = p.norm2[row];
-                const float rn = n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f;
-                ex = n2 > 0.f ? acc * rn : -CUDART_INF_F;            // coarse-key space: dot / |c|
-                sc = fminf(1.f, fmaxf(-1.f, acc * qi.rn_q * rn));
-            } else if (p.metric == ARCHI_IP) {
-                ex = acc;
-                sc = -acc;
-            } else {
-                ex = qi.qn2 - acc;                                   // 2 q.c - |c|^2 = |q|^2 - d^2
-                sc = sqrtf(fmaxf(acc, 0.f));
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) acc[j] += __shfl_xor_sync(kFull, acc[j], d);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (lane == j && cb + j < nk) {
+                float ex, scv;
+                if (p.metric == ARCHI_COSINE) {
+                    const float rn = n2[j] > 0.f ? 1.0f / sqrtf(n2[j]) : 0.f;
+                    ex = n2[j] > 0.f ? acc[j] * rn : -CUDART_INF_F;        // coarse-key space: dot / |c|
+                    scv = fminf(1.f, fmaxf(-1.f, acc[j] * qi.rn_q * rn));
+                } else if (p.metric == ARCHI_IP) {
+                    ex = acc[j];
+                    scv = -acc[j];
+                } else {
+                    ex = qi.qn2 - acc[j];                                  // 2 q.c - |c|^2 = |q|^2 - d^2
+                    scv = sqrtf(fmaxf(acc[j], 0.f));
+                }
+                s_ex[cb + j] = ex;
+                s_sc[cb + j] = scv;
             }
-            s_ex[c] = ex;
-            s_sc[c] = sc;
         }
     }
     __syncthreads();
@@ -1261,7 +1333,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     pp.corpus_rel_err = use_shadow ? 0.001953125f : 0.f;
     pp.cos_raw_unnorm = cos_raw_unnorm;
     pp.norm_dev = norm_dev;
-    ARCHI_CUDA(cudaMemsetAsync(w.unverified + nq_pad, 0, 4, st));
+    pp.n_unverified = w.unverified + nq_pad;
     tc_prep_kernel<<<nq, 128, 0, st>>>(pp);
     ARCHI_CHECK_LAUNCH();
 
@@ -1319,7 +1391,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     bool probed = false;
     if (warm == 1 && n_ctiles >= 8 * ngroups) {
         const int nlists = 2 * ngroups;
-        int cm_slots = (8192 / nlists) / 8 * 8;
+        int cm_slots = (4096 / nlists) / 8 * 8;       // MAXTHR_Q queries x <= 4096 maxima x 4 B of shared memory
         if (cm_slots > 64) cm_slots = 64;
         if (cm_slots < 8) cm_slots = 8;
         static const int probe_div = getenv("ARCHI_TC_PROBE") ? atoi(getenv("ARCHI_TC_PROBE")) : 12;
@@ -1342,9 +1414,13 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         mp.qt_count = qt_count;
         mp.ngroups = ngroups;
         mp.cm_slots = cm_slots;
+        mp.used_slots = per_vcta * 8;
         mp.kprime = kprime;
+        mp.nq = nq;
         mp.thr_g = w.thr_g;
-        tc_maxima_threshold_kernel<<<nq, SEL_THREADS, (size_t)nlists * cm_slots * 4, st>>>(mp);
+        const size_t mt_smem = (size_t)MAXTHR_Q * (round_up(nlists * mp.used_slots, 32) + 4) * 4;
+        ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_maxima_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mt_smem));
+        tc_maxima_threshold_kernel<<<(nq + MAXTHR_Q - 1) / MAXTHR_Q, MAXTHR_THREADS, mt_smem, st>>>(mp);
         ARCHI_CHECK_LAUNCH();
         probed = true;
     }

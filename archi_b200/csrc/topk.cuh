@@ -212,6 +212,76 @@ __device__ __forceinline__ uint32_t block_radix_kth(const uint32_t *keys, int to
     return prefix;
 }
 
+// Warp-level variant of block_radix_kth: one warp, its own 256-bin histogram in shared memory, no
+// block barriers.  keys[] (shared memory) are read lane-strided; every lane of the warp must call it.
+__device__ __forceinline__ uint32_t warp_radix_kth(const uint32_t *keys, int total, int k, int *hist, int lane)
+{
+    uint32_t kmax = 0u, kmin = 0xffffffffu;
+#pragma unroll 8
+    for (int i = lane; i < total; i += 32) {
+        const uint32_t key = keys[i];
+        kmax = max(kmax, key);
+        kmin = min(kmin, key);
+    }
+    kmax = __reduce_max_sync(kFull, kmax);
+    kmin = __reduce_min_sync(kFull, kmin);
+    if (kmax == kmin) return kmax;
+    int top = 32 - __clz(kmax ^ kmin);
+    uint32_t known = top >= 32 ? 0u : ~((1u << top) - 1u);
+    uint32_t prefix = kmax & known;
+    int need = k;
+    while (top > 0) {
+        const int width = top < 8 ? top : 8;
+        const int shift = top - width;
+        const uint32_t dmask = (1u << width) - 1u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hist[j * 32 + lane] = 0;
+        __syncwarp();
+#pragma unroll 8
+        for (int i = lane; i < total; i += 32) {
+            const uint32_t key = keys[i];
+            if ((key & known) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1);
+        }
+        __syncwarp();
+        int h[8], mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[j] = hist[lane * 8 + j];
+            mine += h[j];
+        }
+        int suf = mine;   // inclusive suffix sum over lanes (higher lanes = larger digits)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_down_sync(kFull, suf, d);
+            if (lane + d < 32) suf += o;
+        }
+        const int above = suf - mine;
+        const unsigned who = __ballot_sync(kFull, above < need && suf >= need);
+        const int src = __ffs(who) - 1;
+        int digit = lane * 8, acc = above;
+        bool found = false;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            if (!found) {
+                if (acc + h[j] >= need) {
+                    digit = lane * 8 + j;
+                    found = true;
+                } else {
+                    acc += h[j];
+                }
+            }
+        }
+        digit = __shfl_sync(kFull, digit, src);
+        acc = __shfl_sync(kFull, acc, src);
+        prefix |= (uint32_t)digit << shift;
+        known |= dmask << shift;
+        need -= acc;
+        top = shift;
+        __syncwarp();
+    }
+    return prefix;
+}
+
 template <int NV>
 struct Log2 {
     static constexpr int value = 1 + Log2<NV / 2>::value;
