@@ -216,6 +216,7 @@ struct CoarseParams {
     int trigger;          // a buffer holding at least this many entries is compacted after the tile
     int tile_begin, tile_end;  // corpus tiles [tile_begin, tile_end) are scanned by this launch
     int resume;           // 1: continue from the candidate counts / thresholds left by a previous launch
+    int a_res, a_stages;  // resident query tile: on/off, corpus-chunk stages behind it
     int split;            // 1: both epilogue groups drain every tile, half the columns each
     int maxima_only;      // 1: probe launch -- record the maximum live key of every 32-column chunk, store nothing
     float *chunkmax;      // [grid * 2][cm_slots][BM] chunk maxima of a probe launch
@@ -341,11 +342,19 @@ __device__ __forceinline__ void compact_dispatch(uint2 *buf, int n, int kprime, 
 template <bool TF32, bool TWO, bool RAW>
 __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUtensorMap &tmap_c, const CoarseParams &p)
 {
-    constexpr int STAGES = Geo<TWO>::STAGES;
-    constexpr int STAGE_BYTES = Geo<TWO>::STAGE_BYTES;
+    // Two shared-memory plans.  Streaming (default): a ring of STAGES x (query chunk | corpus chunk).
+    // Resident queries (p.a_res, short rows): the CTA's whole query tile is loaded once and stays at the
+    // bottom of the ring area; the ring behind it only carries corpus chunks.  That halves the L2 -> SM
+    // traffic and the shared-memory writes of a D <= 512 scan.
+    constexpr int B_BYTES = Geo<TWO>::B_BYTES;
+    const bool ares = p.a_res != 0;
+    const int nst = ares ? p.a_stages : Geo<TWO>::STAGES;
+    const int stage_bytes = ares ? B_BYTES : Geo<TWO>::STAGE_BYTES;
+    const int b_off = ares ? 0 : A_BYTES;                    // corpus chunk inside a stage
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = ptx::smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte aligned (128B swizzle atoms)
+    const uint32_t ring = ares ? base + p.kchunks * A_BYTES : base;
     unsigned char *base_ptr = smem_dyn + (base - raw);
     // layout: [STAGES x (A | B)] [aux: EPI_WARPS x BN float2] [barriers, tmem ptr: 256 B]
     float2 *s_aux = reinterpret_cast<float2 *>(base_ptr + RING_BYTES);
@@ -353,6 +362,7 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
     const uint32_t full_bar = bar0, empty_bar = bar0 + 8 * MAX_STAGES;
     const uint32_t tfull_bar = bar0 + 16 * MAX_STAGES, tempty_bar = tfull_bar + 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + RING_BYTES + AUX_BYTES + 16 * MAX_STAGES + 32);
+    const uint32_t afull_bar = bar0 + 16 * MAX_STAGES + 40;  // resident query tile landed
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x % p.qt_count;                 // pair mode: qt_count is even, the pair is (2j, 2j+1)
@@ -363,10 +373,11 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&tmap_q);
         ptx::prefetch_tensormap(&tmap_c);
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
             ptx::mbar_init(full_bar + 8 * s, 1);
             ptx::mbar_init(empty_bar + 8 * s, 1);
         }
+        ptx::mbar_init(afull_bar, 1);
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull_bar + 8 * a, 1);
             // one arrival per epilogue warp that drains the buffer (pair mode: both CTAs' warps release the leader)
@@ -397,22 +408,36 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            if (ares && p.tile_begin + group < p.tile_end) {
+                // the query tile, once (pair mode: the leader's barrier collects both CTAs' tiles)
+                if (TWO) {
+                    if (leader) ptx::mbar_arrive_expect_tx(afull_bar, 2 * p.kchunks * A_BYTES);
+                    const uint32_t afull_leader = ptx::mapa(afull_bar, 0);
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        ptx::tma_load_2d_2sm(base + kc * A_BYTES, &tmap_q, afull_leader, kc * p.kelems, qt * BM);
+                } else {
+                    ptx::mbar_arrive_expect_tx(afull_bar, p.kchunks * A_BYTES);
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        ptx::tma_load_2d(base + kc * A_BYTES, &tmap_q, afull_bar, kc * p.kelems, qt * BM);
+                }
+            }
+            const uint32_t tx_bytes = (uint32_t)((TWO ? 2 : 1) * stage_bytes);
             for (int ct = p.tile_begin + group; ct < p.tile_end; ct += p.ngroups) {
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
-                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint32_t sa = ring + s * stage_bytes;
                     if (TWO) {
                         // the leader's barrier collects the bytes of both CTAs
-                        if (leader) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);
-                        ptx::tma_load_2d_2sm(sa, &tmap_q, full_bar_leader + 8 * s, kc * p.kelems, qt * BM);
-                        ptx::tma_load_2d_2sm(sa + A_BYTES, &tmap_c, full_bar_leader + 8 * s, kc * p.kelems,
+                        if (leader) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx_bytes);
+                        if (!ares) ptx::tma_load_2d_2sm(sa, &tmap_q, full_bar_leader + 8 * s, kc * p.kelems, qt * BM);
+                        ptx::tma_load_2d_2sm(sa + b_off, &tmap_c, full_bar_leader + 8 * s, kc * p.kelems,
                                              ct * BN + (int)cta_rank * (BN / 2));
                     } else {
-                        ptx::mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
-                        ptx::tma_load_2d(sa, &tmap_q, full_bar + 8 * s, kc * p.kelems, qt * BM);
-                        ptx::tma_load_2d(sa + A_BYTES, &tmap_c, full_bar + 8 * s, kc * p.kelems, ct * BN);
+                        ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx_bytes);
+                        if (!ares) ptx::tma_load_2d(sa, &tmap_q, full_bar + 8 * s, kc * p.kelems, qt * BM);
+                        ptx::tma_load_2d(sa + b_off, &tmap_c, full_bar + 8 * s, kc * p.kelems, ct * BN);
                     }
-                    if (++s == STAGES) {
+                    if (++s == nst) {
                         s = 0;
                         ph ^= 1u;
                     }
@@ -433,14 +458,15 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
                 const int acc = u & 1;
                 const uint32_t aph = (uint32_t)(u >> 1) & 1u;
                 ptx::mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);
+                if (ares && u == 0) ptx::mbar_wait(afull_bar, 0u);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(full_bar + 8 * s, ph);
                     ptx::tc_fence_after();
-                    const uint32_t sa = base + s * STAGE_BYTES;
-                    const uint64_t adesc = smem_desc_sw128(sa);
-                    const uint64_t bdesc = smem_desc_sw128(sa + A_BYTES);
+                    const uint32_t sa = ring + s * stage_bytes;
+                    const uint64_t adesc = smem_desc_sw128(ares ? base + kc * A_BYTES : sa);
+                    const uint64_t bdesc = smem_desc_sw128(sa + b_off);
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         if (p.debug & 1) break;
@@ -457,7 +483,7 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
                     // smem stage reusable (in both CTAs) once these MMAs retire
                     if (TWO) ptx::tc_commit_2sm(empty_bar + 8 * s, 3);
                     else ptx::tc_commit(empty_bar + 8 * s);
-                    if (++s == STAGES) {
+                    if (++s == nst) {
                         s = 0;
                         ph ^= 1u;
                     }
@@ -550,6 +576,7 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
             //      (compaction trigger), so a tile cannot overflow the buffer.
             auto process = [&](uint32_t (&r)[32], int c) {
                 uint32_t mask = 0u;
+                if (p.debug & 4) return;                 // timing experiment: TMEM loads only
                 if (p.maxima_only) {
                     // probe launch: the largest key among the live columns of this chunk; the k'-th
                     // largest chunk maximum of a query bounds its final k'-th best key from below
@@ -581,6 +608,7 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
                     const float m0 = fmaxf(fmaxf(m[0], m[1]), m[2]), m1 = fmaxf(fmaxf(m[3], m[4]), m[5]);
                     const float m2 = fmaxf(fmaxf(m[6], m[7]), m[8]), m3 = fmaxf(m[9], m[10]);
                     const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    if (p.debug & 8) return;             // timing experiment: chunk maximum only
                     if (!__any_sync(kFull, mx > thr)) return;
                     const uint32_t live = __shfl_sync(kFull, tile_word, c);
 #pragma unroll
@@ -845,8 +873,19 @@ __device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int 
     const bool staged = total <= SEL_STAGE;
     if (staged) {
         // one walk over global memory, every load independent of the others (this kernel is latency bound)
-        for (int i = tid; i < total; i += SEL_THREADS)
-            s_stage[i] = fmap(__uint_as_float(__ldcg(&sel_locate(c, s_off, nlists, qt, tq, i)->x)));
+        for (int i0 = tid; i0 < total; i0 += 4 * SEL_THREADS) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * SEL_THREADS;
+                if (i < total) v[u] = __ldcg(&sel_locate(c, s_off, nlists, qt, tq, i)->x);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * SEL_THREADS;
+                if (i < total) s_stage[i] = fmap(__uint_as_float(v[u]));
+            }
+        }
         __syncthreads();
         int n_gt;
         return block_radix_kth(s_stage, total, c.kprime, s_hist, s_misc, n_gt);
@@ -1360,6 +1399,13 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         // column-split epilogue: pays when a tile's MMAs are short (measured: D=384 step -8 %, D>=768 +-2 %)
         static const int split = getenv("ARCHI_TC_SPLIT") ? atoi(getenv("ARCHI_TC_SPLIT")) : -1;
         cp.split = split >= 0 ? split : (cp.kchunks * (tf32 ? 2 : 1) <= 8 ? 1 : 0);
+        // resident query tile when it leaves room for at least 4 corpus-chunk stages
+        static const int ares_env = getenv("ARCHI_TC_ARES") ? atoi(getenv("ARCHI_TC_ARES")) : 1;
+        const int b_bytes = (pair ? BN / 2 : BN) * 128;
+        int a_stages = (RING_BYTES - cp.kchunks * A_BYTES) / b_bytes;
+        if (a_stages > MAX_STAGES) a_stages = MAX_STAGES;
+        cp.a_res = ares_env && a_stages >= 4;
+        cp.a_stages = a_stages;
     }
     cp.exit_cap = cap;           // final launch: nothing to bound (the select kernel walks global memory)
     cp.aux = reinterpret_cast<const float2 *>(w.aux);
