@@ -26,7 +26,7 @@ EXPORTS = [
     "archi_store_info", "archi_store_reserve", "archi_store_reset", "archi_store_append",
     "archi_store_delete_rows", "archi_store_read_rows", "archi_store_save", "archi_store_load",
     "archi_pool_normalize", "archi_pool_normalize_append", "archi_search", "archi_hybrid_search",
-    "archi_bm25_accumulate", "archi_merge_topk", "archi_store_last_stats", "archi_store_set_timing",
+    "archi_bm25_accumulate", "archi_merge_topk", "archi_merge_topk_strided", "archi_store_last_stats", "archi_store_set_timing",
 ]
 
 
@@ -82,6 +82,7 @@ def lib() -> ctypes.CDLL:
                                       c_i64, c_p]
     L.archi_bm25_accumulate.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p]
     L.archi_merge_topk.argtypes = [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
+    L.archi_merge_topk_strided.argtypes = [c_i, c_p, c_p, c_i64, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
     L.archi_store_last_stats.argtypes = [c_p, ctypes.POINTER(SearchStats)]
     L.archi_store_set_timing.argtypes = [c_p, c_i]
     for name in EXPORTS:

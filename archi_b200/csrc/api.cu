@@ -657,8 +657,24 @@ int archi_merge_topk(int device, const float *scores_dev, const int64_t *ids_dev
     ARCHI_REQUIRE(nq == 0 || k == 0 || (scores_dev && ids_dev && out_scores_dev && out_ids_dev),
                   "merge_topk: null argument");
     ARCHI_DEVICE_GUARD(device);
-    return launch_merge_lists(scores_dev, ids_dev, n_lists, nq, k, larger_is_better, out_scores_dev, out_ids_dev,
-                              reinterpret_cast<cudaStream_t>(stream));
+    const size_t dense = (size_t)nq * (size_t)k;
+    return launch_merge_lists(scores_dev, ids_dev, dense, dense, n_lists, nq, k, larger_is_better, out_scores_dev,
+                              out_ids_dev, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int archi_merge_topk_strided(int device, const float *scores_dev, const int64_t *ids_dev, int64_t scores_list_stride,
+                             int64_t ids_list_stride, int n_lists, int nq, int k, int larger_is_better,
+                             float *out_scores_dev, int64_t *out_ids_dev, void *stream)
+{
+    ARCHI_REQUIRE(nq >= 0 && k >= 0, "merge_topk_strided: negative size");
+    ARCHI_REQUIRE(nq == 0 || k == 0 || (scores_dev && ids_dev && out_scores_dev && out_ids_dev),
+                  "merge_topk_strided: null argument");
+    ARCHI_REQUIRE(scores_list_stride >= (int64_t)nq * k && ids_list_stride >= (int64_t)nq * k,
+                  "merge_topk_strided: list strides (%lld, %lld) are shorter than one list (%lld elements)",
+                  (long long)scores_list_stride, (long long)ids_list_stride, (long long)nq * k);
+    ARCHI_DEVICE_GUARD(device);
+    return launch_merge_lists(scores_dev, ids_dev, (size_t)scores_list_stride, (size_t)ids_list_stride, n_lists, nq, k,
+                              larger_is_better, out_scores_dev, out_ids_dev, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int archi_store_last_stats(archi_store_t *s, archi_search_stats_t *out)

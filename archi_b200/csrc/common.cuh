@@ -166,7 +166,8 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
                          float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st,
                          int *n_unverified_host, int *unverified_host, double *coarse_ms);
 void free_tensor_workspace(TensorWorkspace &w);
-int launch_merge_lists(const float *scores, const int64_t *ids, int n_lists, int nq, int k,
-                       int larger_is_better, float *out_scores, int64_t *out_ids, cudaStream_t st);
+int launch_merge_lists(const float *scores, const int64_t *ids, size_t scores_list_stride, size_t ids_list_stride,
+                       int n_lists, int nq, int k, int larger_is_better, float *out_scores, int64_t *out_ids,
+                       cudaStream_t st);
 
 }  // namespace archi

@@ -156,15 +156,19 @@ int launch_bm25(const int32_t *doc_ids, const int32_t *tfs, int64_t n_post, floa
 // One warp per query; lane l walks list l (n_lists <= 32); each step a warp arg-best picks the
 // next output.  Works for any k.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) merge_lists_kernel(const float *scores, const long long *ids, int n_lists,
-                                                          int nq, int k, int larger, float *out_scores,
-                                                          long long *out_ids)
+__global__ void __launch_bounds__(128) merge_lists_kernel(const float *scores, const long long *ids,
+                                                          size_t s_stride, size_t i_stride, int n_lists, int nq,
+                                                          int k, int larger, float *out_scores, long long *out_ids)
 {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (q >= nq) return;
     const bool has_list = lane < n_lists;
-    const size_t base = has_list ? ((size_t)lane * nq + q) * k : 0;
+    // list l starts s_stride (i_stride) elements after list l-1: dense [n_lists, nq, k] arrays or the
+    // records of one packed all-gather buffer
+    const size_t in_list = (size_t)q * k;
+    const float *my_scores = scores + (has_list ? (size_t)lane * s_stride + in_list : 0);
+    const long long *my_ids = ids + (has_list ? (size_t)lane * i_stride + in_list : 0);
     int pos = 0;
     for (int out = 0; out < k; ++out) {
         // head of my list
@@ -172,8 +176,8 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float *scores, c
         long long id = -1;
         float sc = CUDART_NAN_F;
         if (has_list && pos < k) {
-            id = ids[base + pos];
-            sc = scores[base + pos];
+            id = my_ids[pos];
+            sc = my_scores[pos];
             if (id >= 0 && sc == sc) key = larger ? sc : -sc;
             else id = -1;
         }
@@ -217,13 +221,15 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float *scores, c
     }
 }
 
-int launch_merge_lists(const float *scores, const int64_t *ids, int n_lists, int nq, int k, int larger_is_better,
-                       float *out_scores, int64_t *out_ids, cudaStream_t st)
+int launch_merge_lists(const float *scores, const int64_t *ids, size_t scores_list_stride, size_t ids_list_stride,
+                       int n_lists, int nq, int k, int larger_is_better, float *out_scores, int64_t *out_ids,
+                       cudaStream_t st)
 {
     ARCHI_REQUIRE(n_lists >= 1 && n_lists <= 32, "merge_topk: n_lists=%d must be in [1, 32]", n_lists);
     if (nq == 0 || k == 0) return ARCHI_OK;
-    merge_lists_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(scores, (const long long *)ids, n_lists, nq, k,
-                                                                 larger_is_better, out_scores, (long long *)out_ids);
+    merge_lists_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(scores, (const long long *)ids, scores_list_stride,
+                                                                 ids_list_stride, n_lists, nq, k, larger_is_better,
+                                                                 out_scores, (long long *)out_ids);
     ARCHI_CHECK_LAUNCH();
     return ARCHI_OK;
 }

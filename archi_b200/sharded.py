@@ -59,8 +59,8 @@ class ShardedStore:
         self.total_rows = 0
 
     # ---- defaults: the CUDA path -------------------------------------------------------------------
-    def _native_search(self, queries, k, id_offset):
-        return self.native.search(queries, k, id_offset=id_offset)
+    def _native_search(self, queries, k, id_offset, out=None):
+        return self.native.search(queries, k, id_offset=id_offset, out=out)
 
     @staticmethod
     def _native_merge(scores, ids, larger_is_better):
@@ -86,6 +86,9 @@ class ShardedStore:
     def search(self, queries, k: int):
         """Every rank passes the same ``queries`` and receives the same merged (scores, ids)."""
         import torch
+        if self.world > 1 and self._local_search == self._native_search and self._merge == self._native_merge \
+                and getattr(queries, "is_cuda", False):
+            return self._search_packed(queries, int(k))
         scores, ids = self._local_search(queries, k, self.id_offset)
         if self.world == 1:
             return scores, ids
@@ -99,4 +102,21 @@ class ShardedStore:
             li = [g_ids[r] for r in range(self.world)]
             self._dist.all_gather(ls, scores.contiguous(), group=self.group)
             self._dist.all_gather(li, ids.contiguous(), group=self.group)
+        return self._merge(g_scores, g_ids, self.larger_is_better)
+
+    def _search_packed(self, queries, k: int):
+        """CUDA path: the local top-k lands directly in this rank's record {ids | scores | pad to 8 B};
+        ONE all-gather moves every record, and the merge kernel reads the gathered buffer in place."""
+        import torch
+        nq = 1 if queries.dim() == 1 else int(queries.shape[0])
+        n = nq * k
+        rec = (n * 12 + 7) // 8 * 8
+        mine = torch.empty(rec, dtype=torch.uint8, device=queries.device)
+        ids = mine[:n * 8].view(torch.int64).view(nq, k)
+        scores = mine[n * 8:n * 12].view(torch.float32).view(nq, k)
+        self._local_search(queries, k, self.id_offset, out=(scores, ids))
+        gathered = torch.empty((self.world, rec), dtype=torch.uint8, device=queries.device)
+        self._dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        g_ids = gathered[:, :n * 8].view(torch.int64).view(self.world, nq, k)
+        g_scores = gathered[:, n * 8:n * 12].view(torch.float32).view(self.world, nq, k)
         return self._merge(g_scores, g_ids, self.larger_is_better)

@@ -163,8 +163,8 @@ class NativeStore:
         buffers; torch CUDA queries -> torch CUDA outputs, nothing synchronised.
         ``filter_mask``: torch CUDA int32/uint32 bitmask words (bit i&31 of word i>>5 = row passes).
         ``hybrid``: scores are the combined score of hybrid_search; ``bm25`` is a torch CUDA fp32
-        [nq, rows] tensor (or None).  ``out``: optional preallocated (scores, ids) host arrays
-        (e.g. views of pinned memory) for the numpy path."""
+        [nq, rows] tensor (or None).  ``out``: optional preallocated (scores, ids) -- host arrays
+        (e.g. views of pinned memory) on the numpy path, contiguous CUDA tensors on the torch path."""
         k = int(k)
         fm = ctypes.c_void_p(filter_mask.data_ptr()) if filter_mask is not None else None
         bm = ctypes.c_void_p(bm25.data_ptr()) if bm25 is not None else None
@@ -174,8 +174,15 @@ class NativeStore:
             if q.dim() == 1:
                 q = q[None, :]
             nq = q.shape[0]
-            scores = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-            ids = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            if out is not None:
+                scores, ids = out
+                if tuple(scores.shape) != (nq, k) or tuple(ids.shape) != (nq, k) or scores.dtype != torch.float32 \
+                        or ids.dtype != torch.int64 or not (scores.is_contiguous() and ids.is_contiguous()) \
+                        or scores.device != q.device or ids.device != q.device:
+                    raise ValueError("out must be contiguous CUDA tensors (float32 [nq,k], int64 [nq,k]) on the query device")
+            else:
+                scores = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+                ids = torch.empty((nq, k), dtype=torch.int64, device=q.device)
             qp, sp, ip_, loc = q.data_ptr(), scores.data_ptr(), ids.data_ptr(), N.DEVICE
             stream = ctypes.c_void_p(_current_stream_ptr(self.device))
         else:
@@ -231,12 +238,20 @@ def pool_normalize(hidden, mask, want_bf16: bool = False, want_f32: bool = True)
 def merge_topk(scores, ids, larger_is_better: bool):
     """scores/ids: torch CUDA [n_lists, nq, k] (each list best first) -> merged [nq, k]."""
     import torch
-    s, i = scores.contiguous(), ids.contiguous()
+
+    def list_strided(t):
+        # dense [nq, k] blocks, any distance between lists (views into one all-gather buffer)
+        return t.dim() == 3 and (t.shape[1] * t.shape[2] == 0 or
+                                 (t.stride(2) == 1 and t.stride(1) == t.shape[2] and t.stride(0) >= t.shape[1] * t.shape[2]))
+
+    s = scores if list_strided(scores) else scores.contiguous()
+    i = ids if list_strided(ids) else ids.contiguous()
     n_lists, nq, k = s.shape
     out_s = torch.empty((nq, k), dtype=torch.float32, device=s.device)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=s.device)
-    N.check(N.lib().archi_merge_topk(s.device.index, ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(i.data_ptr()),
-                                     n_lists, nq, k, int(larger_is_better), ctypes.c_void_p(out_s.data_ptr()),
-                                     ctypes.c_void_p(out_i.data_ptr()),
-                                     ctypes.c_void_p(_current_stream_ptr(s.device.index))))
+    N.check(N.lib().archi_merge_topk_strided(
+        s.device.index, ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(i.data_ptr()),
+        int(s.stride(0)) if n_lists > 1 else nq * k, int(i.stride(0)) if n_lists > 1 else nq * k,
+        n_lists, nq, k, int(larger_is_better), ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_i.data_ptr()),
+        ctypes.c_void_p(_current_stream_ptr(s.device.index))))
     return out_s, out_i

@@ -147,6 +147,15 @@ int archi_merge_topk(int device, const float *scores_dev, const int64_t *ids_dev
                      int nq, int k, int larger_is_better, float *out_scores_dev,
                      int64_t *out_ids_dev, void *stream);
 
+/* Same merge over lists that are not densely packed: list l starts scores_list_stride fp32 elements
+ * (ids_list_stride int64 elements) after list l-1, each list itself a dense [nq, k] block.  This is the
+ * layout of ONE all-gather of per-rank records {ids [nq,k] int64 | scores [nq,k] fp32 | padding}, so
+ * the shard exchange needs a single collective and no repacking. */
+int archi_merge_topk_strided(int device, const float *scores_dev, const int64_t *ids_dev,
+                             int64_t scores_list_stride, int64_t ids_list_stride, int n_lists, int nq,
+                             int k, int larger_is_better, float *out_scores_dev, int64_t *out_ids_dev,
+                             void *stream);
+
 /* Statistics of the last archi_search on this handle (path taken, passes, tensor-path fallbacks). */
 typedef struct {
     int path;              /* ARCHI_PATH_STREAM | ARCHI_PATH_TENSOR */

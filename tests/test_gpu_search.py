@@ -229,6 +229,18 @@ def test_merge_topk_kernel():
         order = np.lexsort((flat_i, -key), axis=1)[:, :k]
         assert np.array_equal(mi, np.take_along_axis(flat_i, order, 1))
         assert np.array_equal(ms, np.take_along_axis(flat_s, order, 1))
+        # the same lists as records {ids | scores | pad} of one all-gather buffer (archi_merge_topk_strided)
+        n = nq * k
+        rec = (n * 12 + 7) // 8 * 8
+        packed = torch.zeros((G, rec), dtype=torch.uint8, device="cuda")
+        p_ids = packed[:, :n * 8].view(torch.int64).view(G, nq, k)
+        p_sc = packed[:, n * 8:n * 12].view(torch.float32).view(G, nq, k)
+        p_ids.copy_(torch.from_numpy(ids))
+        p_sc.copy_(torch.from_numpy(s))
+        assert not p_sc.is_contiguous()
+        ps, pi = merge_topk(p_sc, p_ids, larger)
+        assert np.array_equal(pi.cpu().numpy(), mi)
+        assert np.array_equal(ps.cpu().numpy(), ms, equal_nan=True)
 
 
 def test_full_size_config2_properties():
