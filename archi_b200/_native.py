@@ -27,6 +27,8 @@ EXPORTS = [
     "archi_store_delete_rows", "archi_store_read_rows", "archi_store_save", "archi_store_load",
     "archi_pool_normalize", "archi_pool_normalize_append", "archi_search", "archi_hybrid_search",
     "archi_bm25_accumulate", "archi_merge_topk", "archi_merge_topk_strided", "archi_store_last_stats", "archi_store_set_timing",
+    "archi_exchange_create", "archi_exchange_local_handle", "archi_exchange_connect", "archi_exchange_merge_topk",
+    "archi_exchange_status", "archi_exchange_destroy",
 ]
 
 
@@ -83,6 +85,12 @@ def lib() -> ctypes.CDLL:
     L.archi_bm25_accumulate.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p]
     L.archi_merge_topk.argtypes = [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
     L.archi_merge_topk_strided.argtypes = [c_i, c_p, c_p, c_i64, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
+    L.archi_exchange_create.argtypes = [c_i, c_i, c_i, c_i64, pp]
+    L.archi_exchange_local_handle.argtypes = [c_p, c_p]
+    L.archi_exchange_connect.argtypes = [c_p, c_p]
+    L.archi_exchange_merge_topk.argtypes = [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]
+    L.archi_exchange_status.argtypes = [c_p, pint]
+    L.archi_exchange_destroy.argtypes = [c_p]
     L.archi_store_last_stats.argtypes = [c_p, ctypes.POINTER(SearchStats)]
     L.archi_store_set_timing.argtypes = [c_p, c_i]
     for name in EXPORTS:

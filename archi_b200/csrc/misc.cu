@@ -1,6 +1,7 @@
 // misc.cu -- small kernels around the hot path: row append (convert + |row|^2), tombstones,
 // row read-back, BM25 posting-list accumulation, and the shard-merge of per-GPU k-lists.
 #include "common.cuh"
+#include "merge.cuh"
 #include "topk.cuh"
 
 namespace archi {
@@ -163,62 +164,7 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float *scores, c
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (q >= nq) return;
-    const bool has_list = lane < n_lists;
-    // list l starts s_stride (i_stride) elements after list l-1: dense [n_lists, nq, k] arrays or the
-    // records of one packed all-gather buffer
-    const size_t in_list = (size_t)q * k;
-    const float *my_scores = scores + (has_list ? (size_t)lane * s_stride + in_list : 0);
-    const long long *my_ids = ids + (has_list ? (size_t)lane * i_stride + in_list : 0);
-    int pos = 0;
-    for (int out = 0; out < k; ++out) {
-        // head of my list
-        float key = -CUDART_INF_F;
-        long long id = -1;
-        float sc = CUDART_NAN_F;
-        if (has_list && pos < k) {
-            id = my_ids[pos];
-            sc = my_scores[pos];
-            if (id >= 0 && sc == sc) key = larger ? sc : -sc;
-            else id = -1;
-        }
-        // warp arg-best on (key desc, id asc); exhausted lists carry id -1
-        float bk = key;
-        long long bi = id;
-        int bl = lane;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            const float ok = __shfl_xor_sync(kFull, bk, d);
-            const long long oi = __shfl_xor_sync(kFull, bi, d);
-            const int ol = __shfl_xor_sync(kFull, bl, d);
-            const bool mine_valid = bi >= 0, other_valid = oi >= 0;
-            bool take = false;
-            if (other_valid && !mine_valid) take = true;
-            else if (other_valid && mine_valid)
-                take = ok > bk || (ok == bk && (oi < bi || (oi == bi && ol < bl)));
-            else if (!other_valid && !mine_valid)
-                take = ol < bl;
-            if (take) {
-                bk = ok;
-                bi = oi;
-                bl = ol;
-            }
-        }
-        const float win_sc = __shfl_sync(kFull, sc, bl);
-        if (lane == 0) {
-            out_scores[(size_t)q * k + out] = bi >= 0 ? win_sc : CUDART_NAN_F;
-            out_ids[(size_t)q * k + out] = bi;
-        }
-        if (bi < 0) {
-            // every list is exhausted: pad the rest
-            if (lane == 0)
-                for (int o = out + 1; o < k; ++o) {
-                    out_scores[(size_t)q * k + o] = CUDART_NAN_F;
-                    out_ids[(size_t)q * k + o] = -1;
-                }
-            break;
-        }
-        if (lane == bl) ++pos;
-    }
+    merge_query_lists(scores, ids, s_stride, i_stride, n_lists, nq, q, k, larger, out_scores, out_ids, lane);
 }
 
 int launch_merge_lists(const float *scores, const int64_t *ids, size_t scores_list_stride, size_t ids_list_stride,

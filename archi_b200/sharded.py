@@ -7,6 +7,11 @@ all-gather (``Q*k*12`` bytes per rank over NVLink) and merged on the device by
 ``archi_merge_topk``.  Exact because the global top-k is a subset of the union of the local ones.
 
 The exchange step is the only collective; there is none on the data path of the scan itself.
+
+On one box the exchange does not go through NCCL at all when the ranks can map each other's memory
+(CUDA IPC): ``PeerExchange`` pushes every rank's record straight into its peers' HBM over NVLink and
+merges in the same kernel (csrc/exchange.cu).  It is validated against the NCCL path when it is set up
+and switched off (with a warning) if the box cannot do it; ``ARCHI_PEER_EXCHANGE=0`` forces NCCL.
 """
 from __future__ import annotations
 
@@ -35,6 +40,69 @@ def offsets_from_counts(counts: Sequence[int]) -> List[int]:
     return out
 
 
+class PeerExchange:
+    """Handle of archi_exchange_* (include/archi_b200.h): one gather buffer per rank, mapped by every
+    peer.  Construction is collective over ``group``; raises RuntimeError on every rank if any rank
+    cannot map its peers."""
+
+    def __init__(self, device_index: int, rank: int, world: int, group, max_record_bytes: int):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        self._N, self._ctypes, self._dist, self.group = N, ctypes, dist, group
+        self.device_index, self.rank, self.world = int(device_index), int(rank), int(world)
+        self.max_record_bytes = int(max_record_bytes)
+        L = N.lib()
+        h = ctypes.c_void_p()
+        N.check(L.archi_exchange_create(self.device_index, self.rank, self.world, self.max_record_bytes, ctypes.byref(h)))
+        self._h = h
+        dev = torch.device("cuda", self.device_index)
+        raw = (ctypes.c_ubyte * 64)()
+        N.check(L.archi_exchange_local_handle(h, raw))
+        mine = torch.tensor(list(bytes(raw)), dtype=torch.uint8, device=dev)
+        handles = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(handles, mine, group=group)
+        blob = handles.cpu().numpy().tobytes()
+        rc = L.archi_exchange_connect(h, blob)
+        why = "" if rc == 0 else L.archi_last_error().decode("utf-8", "replace")
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close(barrier=False)
+            raise RuntimeError("peer-memory exchange unavailable: " + (why or "a peer rank could not map this rank's buffer"))
+
+    def merge_topk(self, record, nq: int, k: int, larger_is_better: bool):
+        """record: uint8 CUDA tensor {ids [nq,k] int64 | scores [nq,k] fp32} of this rank.  Returns the
+        merged (scores [nq,k], ids [nq,k]) of all ranks; stream-ordered, nothing synchronised."""
+        import torch
+        ctypes, N = self._ctypes, self._N
+        dev = record.device
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        stream = ctypes.c_void_p(int(torch.cuda.current_stream(dev).cuda_stream))
+        N.check(N.lib().archi_exchange_merge_topk(self._h, ctypes.c_void_p(record.data_ptr()), int(nq), int(k),
+                                                  int(larger_is_better), ctypes.c_void_p(out_s.data_ptr()),
+                                                  ctypes.c_void_p(out_i.data_ptr()), stream))
+        return out_s, out_i
+
+    def timed_out(self) -> bool:
+        """Synchronises the device; True if any call gave up waiting for a peer."""
+        flag = self._ctypes.c_int(0)
+        self._N.check(self._N.lib().archi_exchange_status(self._h, self._ctypes.byref(flag)))
+        return flag.value != 0
+
+    def close(self, barrier: bool = True) -> None:
+        if getattr(self, "_h", None) is None:
+            return
+        if barrier:
+            import torch
+            torch.cuda.synchronize(self.device_index)
+            self._dist.barrier(group=self.group)      # nobody may still be pushing into a buffer about to be freed
+        self._N.lib().archi_exchange_destroy(self._h)
+        self._h = None
+
+
 class ShardedStore:
     """``local_search(queries, k, id_offset) -> (scores [nq,k], ids [nq,k])`` and
     ``merge(scores [G,nq,k], ids [G,nq,k], larger_is_better) -> (scores, ids)`` default to the
@@ -57,6 +125,8 @@ class ShardedStore:
         self._local_rows = local_rows or (lambda: self.native.rows())
         self.id_offset = 0
         self.total_rows = 0
+        self._exchange = None           # PeerExchange, or False once found unavailable
+        self.exchange_kind = "nccl"     # what search() uses between the ranks: "nccl" | "peer-memory"
 
     # ---- defaults: the CUDA path -------------------------------------------------------------------
     def _native_search(self, queries, k, id_offset, out=None):
@@ -105,18 +175,82 @@ class ShardedStore:
         return self._merge(g_scores, g_ids, self.larger_is_better)
 
     def _search_packed(self, queries, k: int):
-        """CUDA path: the local top-k lands directly in this rank's record {ids | scores | pad to 8 B};
+        """CUDA path: the local top-k lands directly in this rank's record {ids | scores | pad to 16 B};
         ONE all-gather moves every record, and the merge kernel reads the gathered buffer in place."""
         import torch
         nq = 1 if queries.dim() == 1 else int(queries.shape[0])
         n = nq * k
-        rec = (n * 12 + 7) // 8 * 8
+        rec = (n * 12 + 15) // 16 * 16      # the exchange kernel moves 16-byte words
         mine = torch.empty(rec, dtype=torch.uint8, device=queries.device)
         ids = mine[:n * 8].view(torch.int64).view(nq, k)
         scores = mine[n * 8:n * 12].view(torch.float32).view(nq, k)
         self._local_search(queries, k, self.id_offset, out=(scores, ids))
+        exchange = self._peer_exchange(queries.device, rec)
+        if exchange is not None:
+            return exchange.merge_topk(mine, nq, k, self.larger_is_better)
         gathered = torch.empty((self.world, rec), dtype=torch.uint8, device=queries.device)
         self._dist.all_gather_into_tensor(gathered, mine, group=self.group)
         g_ids = gathered[:, :n * 8].view(torch.int64).view(self.world, nq, k)
         g_scores = gathered[:, n * 8:n * 12].view(torch.float32).view(self.world, nq, k)
         return self._merge(g_scores, g_ids, self.larger_is_better)
+
+    # ---- peer-memory exchange (one box, CUDA IPC) --------------------------------------------------
+    def _peer_exchange(self, device, rec_bytes: int):
+        """The PeerExchange to use for records of ``rec_bytes``, or None (NCCL).  Collective: every rank
+        reaches the same decision at the same call."""
+        import os
+        if self._exchange is False:
+            return None
+        if self._exchange is not None and self._exchange.max_record_bytes >= rec_bytes:
+            return self._exchange
+        if os.environ.get("ARCHI_PEER_EXCHANGE", "1") == "0":
+            self._exchange = False
+            return None
+        if self._exchange is not None:
+            self._exchange.close()
+            self._exchange = None
+        try:
+            ex = PeerExchange(device.index, self.rank, self.world, self.group, max(rec_bytes, 1 << 16))
+            self._validate_exchange(ex, device)
+            self._exchange, self.exchange_kind = ex, "peer-memory"
+        except RuntimeError as e:
+            if self.rank == 0:
+                import warnings
+                warnings.warn(f"archi_b200: {e}; the shard exchange stays on NCCL")
+            self._exchange, self.exchange_kind = False, "nccl"
+            return None
+        return self._exchange
+
+    def _validate_exchange(self, ex: "PeerExchange", device) -> None:
+        """One exchange of synthetic lists, checked against NCCL all-gather + archi_merge_topk_strided."""
+        import torch
+        nq, k = 5, 7
+        n = nq * k
+        rec = (n * 12 + 15) // 16 * 16
+        g = torch.Generator(device="cpu").manual_seed(1234 + self.rank)
+        sc = torch.sort(torch.rand((nq, k), generator=g), dim=1, descending=self.larger_is_better).values
+        mine = torch.zeros(rec, dtype=torch.uint8, device=device)
+        mine[:n * 8].view(torch.int64).view(nq, k).copy_(torch.arange(n).view(nq, k) + 1000 * self.rank)
+        mine[n * 8:n * 12].view(torch.float32).view(nq, k).copy_(sc)
+        got_s, got_i = ex.merge_topk(mine, nq, k, self.larger_is_better)
+        gathered = torch.empty((self.world, rec), dtype=torch.uint8, device=device)
+        self._dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        want_s, want_i = self._merge(gathered[:, n * 8:n * 12].view(torch.float32).view(self.world, nq, k),
+                                     gathered[:, :n * 8].view(torch.int64).view(self.world, nq, k), self.larger_is_better)
+        bad = ex.timed_out() or not (torch.equal(got_i, want_i) and torch.equal(got_s, want_s))
+        flag = torch.tensor([1 if bad else 0], dtype=torch.int32, device=device)
+        self._dist.all_reduce(flag, op=self._dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()):
+            ex.close()
+            raise RuntimeError("peer-memory exchange failed its self-check against the NCCL path")
+
+    def check(self) -> None:
+        """Synchronises; raises if a peer-memory exchange ever timed out (its results were invalid)."""
+        if self._exchange and self._exchange.timed_out():
+            raise RuntimeError("archi_b200: a peer-memory shard exchange timed out waiting for a rank")
+
+    def close(self) -> None:
+        if self._exchange:
+            self._exchange.close()
+        self._exchange = None
+

@@ -159,10 +159,30 @@ def run_reference(args, rows, dim, storage, k, batch, desc):
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference engine (PostgreSQL+pgvector) not installable here; oracle.c restates its seq-scan path"}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON record: keep the real stdout aside and point fd 1 at
+    stderr for everything else (NCCL prints its version banner on stdout from native code)."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line) -> None:
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -357,6 +377,7 @@ def main():
                     "sample": f"{sample_q} queries x {rows}x{dim} fp32 rows, oracle.c (restated pgvector seq scan + heap top-k, pgvector's -march=native -fassociative-math flags), one query per thread"}
         del corpus_h
 
+    sharded.check()      # a peer-memory exchange that timed out would have produced invalid results
     if rank == 0:
         line = {
             "metric": METRIC, "value": batch / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
@@ -367,6 +388,10 @@ def main():
             "data": "synthetic",
             "config": {"workload": desc, "rows": total_rows, "rows_per_gpu": cnt, "dim": dim, "k": k, "batch": batch,
                        "storage": storage, "metric": "cosine", "sharding": f"rows/{world}",
+                       "shard_exchange": ("none (1 GPU)" if world == 1 else
+                                          "one kernel: push k-lists into peers' HBM over NVLink (CUDA IPC), wait, merge"
+                                          if sharded.exchange_kind == "peer-memory" else
+                                          "NCCL all_gather_into_tensor of packed k-lists + merge kernel"),
                        "l2_policy": f"corpus shard {cnt * dim * elt / 1e6:.0f} MB per pass vs 126 MB L2 (no flush needed)"
                        if cnt * dim * elt > 4 * 126e6 else "shard smaller than 4x L2: numbers include L2 hits"},
             "e2e": {"value": batch / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": batch * dim * 4,
@@ -374,7 +399,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu_base, "clocks": clocks, "batches": batches,
         }
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
+    sharded.close()
     store.close()
     if world > 1:
         dist.destroy_process_group()

@@ -156,6 +156,33 @@ int archi_merge_topk_strided(int device, const float *scores_dev, const int64_t 
                              int k, int larger_is_better, float *out_scores_dev, int64_t *out_ids_dev,
                              void *stream);
 
+/* ---- shard exchange + merge in one kernel over NVLink peer memory --------------------------
+ * Replaces "all-gather the per-rank k-lists with NCCL, then archi_merge_topk_strided" for the ranks
+ * of one box that can map each other's memory (CUDA IPC; one process per GPU).  No counterpart in the
+ * reference, which is single-backend.  Set-up, once per process group:
+ *   archi_exchange_create        allocate this rank's gather buffer ([2][world][max_record_bytes] + flags)
+ *   archi_exchange_local_handle  64-byte IPC handle of that buffer; all-gather the handles over any
+ *                                transport (torch.distributed, MPI, a file)
+ *   archi_exchange_connect       handles [world][64] indexed by rank -> map every peer's buffer
+ *                                (ARCHI_EUNSUPPORTED when peer mapping is impossible: keep using NCCL)
+ * Per search, on every rank, in the same order, on one stream:
+ *   archi_exchange_merge_topk    record_dev = {ids [nq,k] int64 | scores [nq,k] fp32}, 16-byte aligned,
+ *                                on the device; it is pushed into every peer's buffer, the kernel waits
+ *                                (bounded, 5 s) for all world records of this call and writes the merged
+ *                                [nq,k] lists.  larger_is_better as in archi_merge_topk.
+ *   archi_exchange_status        synchronises the device; *timed_out = 1 if any call gave up waiting
+ *                                (its outputs are then invalid).
+ * archi_exchange_destroy must be preceded by a barrier across the ranks. */
+#define ARCHI_EXCHANGE_HANDLE_BYTES 64
+typedef struct archi_exchange archi_exchange_t;
+int archi_exchange_create(int device, int rank, int world, int64_t max_record_bytes, archi_exchange_t **out);
+int archi_exchange_local_handle(archi_exchange_t *x, void *handle_out);
+int archi_exchange_connect(archi_exchange_t *x, const void *handles);
+int archi_exchange_merge_topk(archi_exchange_t *x, const void *record_dev, int nq, int k, int larger_is_better,
+                              float *out_scores_dev, int64_t *out_ids_dev, void *stream);
+int archi_exchange_status(archi_exchange_t *x, int *timed_out);
+int archi_exchange_destroy(archi_exchange_t *x);
+
 /* Statistics of the last archi_search on this handle (path taken, passes, tensor-path fallbacks). */
 typedef struct {
     int path;              /* ARCHI_PATH_STREAM | ARCHI_PATH_TENSOR */

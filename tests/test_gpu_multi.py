@@ -1,5 +1,7 @@
-"""Multi-GPU parity: corpus row-sharded over 2 GPUs (one process per GPU, NCCL all-gather of the
-per-shard k-lists, device merge) against the oracle on the whole corpus.  Skipped on a 1-GPU box."""
+"""Multi-GPU parity: corpus row-sharded over 2 GPUs (one process per GPU; the per-shard k-lists are
+exchanged by the peer-memory kernel where the box allows it and by an NCCL all-gather otherwise, then
+merged on the device) against the oracle on the whole corpus.  Both exchange paths are run and must
+agree bit for bit.  Skipped on a 1-GPU box."""
 import os
 import socket
 import sys
@@ -30,6 +32,7 @@ def _worker(rank, world, port, tmp):
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     ok = True
+    kinds = set()
     for metric, storage, nq, k in (("cosine", "f32", 5, 10), ("l2", "bf16", 40, 7), ("inner_product", "f32", 130, 100)):
         rng = np.random.default_rng(7)
         corpus = rng.standard_normal((30001, 96)).astype(np.float32)
@@ -40,7 +43,23 @@ def _worker(rank, world, port, tmp):
         sh = ShardedStore(store)
         sh.sync_layout(device=torch.device("cuda", rank))
         ok = ok and sh.id_offset == first and sh.total_rows == corpus.shape[0]
-        s, i = sh.search(torch.from_numpy(queries).cuda(), k)
+        q_dev = torch.from_numpy(queries).cuda()
+        s, i = sh.search(q_dev, k)
+        # repeated calls walk through both buffer parities of the peer-memory exchange
+        for rep in range(5):
+            s2, i2 = sh.search(q_dev.flip(0) if rep % 2 == 0 else q_dev, k)
+            if rep % 2 == 0:
+                s2, i2 = s2.flip(0), i2.flip(0)
+            ok = ok and torch.equal(i2, i) and torch.equal(s2, s)
+        sh.check()
+        kinds.add(sh.exchange_kind)
+        # the NCCL path must give the same bits
+        os.environ["ARCHI_PEER_EXCHANGE"] = "0"
+        sh_nccl = ShardedStore(store)
+        sh_nccl.sync_layout(device=torch.device("cuda", rank))
+        s3, i3 = sh_nccl.search(q_dev, k)
+        ok = ok and sh_nccl.exchange_kind == "nccl" and torch.equal(i3, i) and torch.equal(s3, s)
+        del os.environ["ARCHI_PEER_EXCHANGE"]
         torch.cuda.synchronize()
         s, i = s.cpu().numpy(), i.cpu().numpy()
         stored = orc.bf16_bits_to_f32(orc.f32_to_bf16_bits(corpus)) if storage == "bf16" else corpus
@@ -49,8 +68,10 @@ def _worker(rank, world, port, tmp):
         for q in range(nq):
             ok = ok and orc.same_topk_up_to_ties(i[q].tolist(), i_true[q], d_true[q], rel_tol=2e-6, abs_tol=1e-7)
         ok = ok and np.allclose(s, orc.score_from_distance(metric, d_true), rtol=rel, atol=1e-5)
+        sh.close()
         store.close()
-    open(os.path.join(tmp, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").close()
+    with open(os.path.join(tmp, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w") as f:
+        f.write(",".join(sorted(kinds)))
     dist.destroy_process_group()
 
 
@@ -61,3 +82,4 @@ def test_sharded_search_nccl_world2(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]
+    print("shard exchange used:", open(os.path.join(tmp_path, "rank0.ok")).read())
