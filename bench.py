@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (rows, dim, storage, k, default batch, description)
     "c2": (1_000_000, 384, "f32", 10, 1024, "configs[1]: synthetic 1M x 384 fp32 unit-norm chunks, top-10"),
+    "c2s8": (125_000, 384, "f32", 10, 1024, "one shard of configs[1] at 8 GPUs (125k x 384 fp32) on one GPU: exercises the L2-flush policy, not a bench line"),
     "c3": (10_000_000, 768, "bf16", 10, 1024, "configs[2]: synthetic 10M x 768 bf16 chunks, top-10, row-sharded"),
     "c4s": (12_500_000, 1024, "bf16", 100, 1024, "configs[3] one shard: 12.5M x 1024 bf16 chunks per GPU (of 100M over 8), top-100"),
     "c4": (100_000_000, 1024, "bf16", 100, 1024, "configs[3]: synthetic 100M x 1024 bf16 chunks (204.8 GB) row-sharded, top-100"),
@@ -222,7 +223,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg_id = {"c2": 2, "c3": 3, "c4s": 4, "c4": 4}[args.workload]
+    cfg_id = {"c2": 2, "c2s8": 2, "c3": 3, "c4s": 4, "c4": 4}[args.workload]
     if args.sub_batches is None:
         args.sub_batches = "1,64" if world == 1 else ""
     # strong scaling: the corpus is fixed, rank r holds rows [first, first+cnt)
@@ -255,6 +256,15 @@ def main():
     elt = 2 if storage == "bf16" else 4
     peaks = measured_peaks()
 
+    # Timing rule: inputs larger than L2, or an L2 flush between timed iterations.  What a step reads
+    # per GPU is the shard (the bf16 shadow of an fp32 shard on the tensor path); when that is not at
+    # least 2x the 126 MB L2 (strong scaling shrinks it), every timed step is followed by a flush
+    # (a 256 MB memset) + synchronize, and the same loop with the flush alone is subtracted.
+    L2_BYTES = 126e6
+    shard_read_bytes = cnt * dim * (2 if storage == "bf16" or os.environ.get("ARCHI_NO_SHADOW", "0") == "0" else 4)
+    flush_l2 = shard_read_bytes < 2 * L2_BYTES
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_l2 else None
+
     def time_device(q_dev, steps, warmup):
         for _ in range(warmup):
             sharded.search(q_dev, k)
@@ -264,9 +274,22 @@ def main():
         e0.record()
         for _ in range(steps):
             sharded.search(q_dev, k)
+            if flush_l2:
+                flush_buf.zero_()
+                torch.cuda.synchronize()
         e1.record()
         barrier()
-        return max_over_ranks(e0.elapsed_time(e1)) / steps, (N.kernel_launches() - l0)
+        launches = N.kernel_launches() - l0
+        total = e0.elapsed_time(e1)
+        if flush_l2:
+            e0.record()
+            for _ in range(steps):
+                flush_buf.zero_()
+                torch.cuda.synchronize()
+            e1.record()
+            barrier()
+            total -= e0.elapsed_time(e1)
+        return max_over_ranks(total) / steps, launches
 
     def kernel_roofline(q_dev, reps=5):
         """Average CUDA-event duration of the dominant kernel (events recorded inside the library
@@ -343,8 +366,19 @@ def main():
         t0 = time.perf_counter()
         for _ in range(steps):
             one()
+            if flush_l2:
+                flush_buf.zero_()
+                torch.cuda.synchronize()
         barrier()
-        return max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+        total = (time.perf_counter() - t0) * 1e3
+        if flush_l2:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                flush_buf.zero_()
+                torch.cuda.synchronize()
+            barrier()
+            total -= (time.perf_counter() - t0) * 1e3
+        return max_over_ranks(total) / steps
 
     q_dev = make_queries(batch)
     clk = ClockSampler(local_rank)
@@ -392,8 +426,10 @@ def main():
                                           "one kernel: push k-lists into peers' HBM over NVLink (CUDA IPC), wait, merge"
                                           if sharded.exchange_kind == "peer-memory" else
                                           "NCCL all_gather_into_tensor of packed k-lists + merge kernel"),
-                       "l2_policy": f"corpus shard {cnt * dim * elt / 1e6:.0f} MB per pass vs 126 MB L2 (no flush needed)"
-                       if cnt * dim * elt > 4 * 126e6 else "shard smaller than 4x L2: numbers include L2 hits"},
+                       "l2_policy": (f"a step reads {shard_read_bytes / 1e6:.0f} MB per GPU vs 126 MB L2: no flush needed"
+                                     if not flush_l2 else
+                                     f"a step reads only {shard_read_bytes / 1e6:.0f} MB per GPU: L2 flushed (256 MB memset + "
+                                     "synchronize) after every timed step, flush-only loop subtracted")},
             "e2e": {"value": batch / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": batch * dim * 4,
                     "d2h_bytes_per_step": batch * k * 12, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
