@@ -54,21 +54,35 @@ class PeerExchange:
         self.device_index, self.rank, self.world = int(device_index), int(rank), int(world)
         self.max_record_bytes = int(max_record_bytes)
         L = N.lib()
-        h = ctypes.c_void_p()
-        N.check(L.archi_exchange_create(self.device_index, self.rank, self.world, self.max_record_bytes, ctypes.byref(h)))
-        self._h = h
         dev = torch.device("cuda", self.device_index)
+        self._h = None
+
+        def everyone_ok(ok: bool) -> bool:
+            # every step that can fail locally is followed by a collective verdict, so that no rank is
+            # left waiting in a collective the failing rank never enters
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return int(t.item()) == 1
+
+        why = ""
         raw = (ctypes.c_ubyte * 64)()
-        N.check(L.archi_exchange_local_handle(h, raw))
+        h = ctypes.c_void_p()
+        if L.archi_exchange_create(self.device_index, self.rank, self.world, self.max_record_bytes, ctypes.byref(h)) == 0:
+            self._h = h
+            if L.archi_exchange_local_handle(h, raw) != 0:
+                why = L.archi_last_error().decode("utf-8", "replace")
+        else:
+            why = L.archi_last_error().decode("utf-8", "replace")
+        if not everyone_ok(why == ""):
+            self.close(barrier=False)
+            raise RuntimeError("peer-memory exchange unavailable: " + (why or "a peer rank could not export its buffer"))
         mine = torch.tensor(list(bytes(raw)), dtype=torch.uint8, device=dev)
         handles = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(handles, mine, group=group)
         blob = handles.cpu().numpy().tobytes()
-        rc = L.archi_exchange_connect(h, blob)
-        why = "" if rc == 0 else L.archi_last_error().decode("utf-8", "replace")
-        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 0:
+        if L.archi_exchange_connect(h, blob) != 0:
+            why = L.archi_last_error().decode("utf-8", "replace")
+        if not everyone_ok(why == ""):
             self.close(barrier=False)
             raise RuntimeError("peer-memory exchange unavailable: " + (why or "a peer rank could not map this rank's buffer"))
 
@@ -232,12 +246,20 @@ class ShardedStore:
         mine = torch.zeros(rec, dtype=torch.uint8, device=device)
         mine[:n * 8].view(torch.int64).view(nq, k).copy_(torch.arange(n).view(nq, k) + 1000 * self.rank)
         mine[n * 8:n * 12].view(torch.float32).view(nq, k).copy_(sc)
-        got_s, got_i = ex.merge_topk(mine, nq, k, self.larger_is_better)
+        bad = False
+        try:
+            got_s, got_i = ex.merge_topk(mine, nq, k, self.larger_is_better)
+        except RuntimeError:
+            bad = True
+        # the collectives below are entered by every rank whatever happened locally
         gathered = torch.empty((self.world, rec), dtype=torch.uint8, device=device)
         self._dist.all_gather_into_tensor(gathered, mine, group=self.group)
-        want_s, want_i = self._merge(gathered[:, n * 8:n * 12].view(torch.float32).view(self.world, nq, k),
-                                     gathered[:, :n * 8].view(torch.int64).view(self.world, nq, k), self.larger_is_better)
-        bad = ex.timed_out() or not (torch.equal(got_i, want_i) and torch.equal(got_s, want_s))
+        try:
+            want_s, want_i = self._merge(gathered[:, n * 8:n * 12].view(torch.float32).view(self.world, nq, k),
+                                         gathered[:, :n * 8].view(torch.int64).view(self.world, nq, k), self.larger_is_better)
+            bad = bad or ex.timed_out() or not (torch.equal(got_i, want_i) and torch.equal(got_s, want_s))
+        except RuntimeError:
+            bad = True
         flag = torch.tensor([1 if bad else 0], dtype=torch.int32, device=device)
         self._dist.all_reduce(flag, op=self._dist.ReduceOp.MAX, group=self.group)
         if int(flag.item()):

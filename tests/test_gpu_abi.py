@@ -89,3 +89,45 @@ def test_bf16_snapshot_roundtrip(tmp_path):
     after = t.search(q, 5)
     assert np.array_equal(before[1], after[1]) and np.array_equal(before[0], after[0])
     t.close()
+
+
+def test_exchange_abi_single_rank():
+    """archi_exchange_* with world = 1: the kernel pushes the record into its own buffer, signals
+    itself and 'merges' one list -- the output must be the input list (repeated calls alternate the two
+    buffer parities); argument errors are reported, not executed."""
+    import torch
+    from archi_b200 import _native as N
+    L = N.lib()
+    nq, k = 37, 10
+    n = nq * k
+    rec = (n * 12 + 15) // 16 * 16
+    h = ctypes.c_void_p()
+    assert L.archi_exchange_create(0, 0, 1, rec, ctypes.byref(h)) == 0, L.archi_last_error()
+    assert L.archi_exchange_create(0, 3, 2, rec, ctypes.byref(ctypes.c_void_p())) == -1       # rank >= world
+    raw = (ctypes.c_ubyte * 64)()
+    assert L.archi_exchange_local_handle(h, raw) == 0
+    rng = np.random.default_rng(8)
+    stream = ctypes.c_void_p(int(torch.cuda.current_stream().cuda_stream))
+    for call in range(4):
+        for larger in (1, 0):
+            sc = rng.standard_normal((nq, k)).astype(np.float32)
+            sc = -np.sort(-sc, axis=1) if larger else np.sort(sc, axis=1)
+            ids = rng.permutation(n).reshape(nq, k).astype(np.int64)
+            sc[5, 6:], ids[5, 6:] = np.nan, -1                          # a short list
+            mine = torch.zeros(rec, dtype=torch.uint8, device="cuda")
+            mine[:n * 8].view(torch.int64).view(nq, k).copy_(torch.from_numpy(ids))
+            mine[n * 8:n * 12].view(torch.float32).view(nq, k).copy_(torch.from_numpy(sc))
+            out_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+            out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+            rc = L.archi_exchange_merge_topk(h, ctypes.c_void_p(mine.data_ptr()), nq, k, larger,
+                                             ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_i.data_ptr()), stream)
+            assert rc == 0, L.archi_last_error()
+            timed_out = ctypes.c_int(-1)
+            assert L.archi_exchange_status(h, ctypes.byref(timed_out)) == 0 and timed_out.value == 0
+            assert np.array_equal(out_i.cpu().numpy(), ids)
+            assert np.array_equal(out_s.cpu().numpy(), sc, equal_nan=True)
+    too_big = torch.zeros(4 * rec, dtype=torch.uint8, device="cuda")
+    rc = L.archi_exchange_merge_topk(h, ctypes.c_void_p(too_big.data_ptr()), nq * 4, k, 1,
+                                     ctypes.c_void_p(too_big.data_ptr()), ctypes.c_void_p(too_big.data_ptr()), stream)
+    assert rc == -1 and b"exceeds the slot" in L.archi_last_error()
+    assert L.archi_exchange_destroy(h) == 0
