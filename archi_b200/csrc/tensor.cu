@@ -8,15 +8,18 @@
 //                         eps on |coarse key - exact key|.
 //   2. tc_aux_kernel      per-row epilogue constants (a, b): key = dot * a + b  (cosine: a = 1/|c|;
 //                         l2: a = 2, b = -|c|^2; ip: a = 1); masked / deleted rows get b = -inf.
-//   3. tc_coarse_kernel   persistent warp-specialised GEMM.  One CTA per SM: warp 0 = TMA producer
-//                         (128B-swizzled tiles of 128 queries and 256 corpus rows through a 4-stage
-//                         mbarrier ring), warp 1 = tcgen05.mma issuer (M=128 queries x N=256 rows,
-//                         fp32 accumulators double-buffered in TMEM, 2 x 256 columns), warps 2-5 =
-//                         epilogue: tcgen05.ld the 128 x 256 scores, one query per thread, and keep
-//                         only keys above that query's running threshold in a per-(CTA, query)
-//                         candidate buffer; when a buffer fills, the owning warp selects its k' best
-//                         by a ballot/REDUX bisection on the key bits and raises the threshold
-//                         (shared between CTAs through an atomicMax word per query).
+//   3. tc_coarse_kernel   persistent warp-specialised GEMM.  One CTA per SM (or a CTA pair with
+//                         cta_group::2, M = 256): warp 0 = TMA producer (128B-swizzled tiles of 128
+//                         queries and 256 corpus rows through an mbarrier ring; short rows keep the
+//                         query tile resident), warp 1 = tcgen05.mma issuer (fp32 accumulators
+//                         double-buffered in TMEM, 2 x 256 columns), warps 2-9 = two epilogue groups:
+//                         tcgen05.ld the scores, one query per thread, and keep only keys above that
+//                         query's threshold in a per-(CTA, group, query) candidate buffer; when a
+//                         buffer fills, the owning warp selects its k' best by a ballot/REDUX
+//                         bisection on the key bits and raises the threshold (shared between CTAs
+//                         through an atomicMax word per query).  A first PROBE launch of the same
+//                         kernel over ~1/12 of the rows only records chunk maxima, from which
+//                         tc_maxima_threshold_kernel derives the thresholds the main scan starts with.
 //   4. tc_select_kernel   per query: union of the candidate buffers -> k' best coarse keys -> exact
 //                         fp32 rescoring against the stored rows -> top-k, plus the proof that no
 //                         rejected row can belong to the exact top-k:  e_k > T + eps.  Queries that
@@ -1420,20 +1423,18 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     else kern = tf32 ? (raw ? tc_coarse_kernel<true, true> : tc_coarse_kernel<true, false>)
                      : (raw ? tc_coarse_kernel<false, true> : tc_coarse_kernel<false, false>);
     ARCHI_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    // Warm-up phases.  Thresholds local to one (CTA, epilogue group) only ever see 1/(2*ngroups) of
-    // the rows, so most of a plain run is spent storing candidates that a global view would reject.
-    // Instead: (1) every epilogue group scans ONE tile and keeps everything; tc_threshold_kernel turns
-    // the union of all lists into one shared threshold per query (the kprime-th best of those rows --
-    // a valid lower bound of the final one); (2) the same after ~1/16 of the corpus; (3) the rest of
-    // the corpus then runs with thresholds ~2*ngroups times tighter than local ones and its epilogue
-    // almost never stores.  ARCHI_TC_WARM=0 disables the scheme.
+    // Thresholds local to one (CTA, epilogue group) only ever see 1/(2*ngroups) of the rows, so most of
+    // a plain run would be spent storing candidates that a global view rejects.  The scan therefore
+    // starts from ONE shared threshold per query, derived from a small sample of the corpus.
     static const int warm = getenv("ARCHI_TC_WARM") ? atoi(getenv("ARCHI_TC_WARM")) : 1;
     // warm == 1 (default): PROBE scheme.  A first launch scans a small prefix of the corpus (about
     // 1/12, at most 8 tiles per epilogue group) and only records the maximum live key of every
     // 32-column chunk; tc_maxima_threshold_kernel turns the kprime-th largest chunk maximum of each
     // query into its shared threshold; one main launch then scans everything.  No flood of
-    // candidates, no resume.  warm == 2: the older flood + resume phases (kept for comparison);
-    // warm == 0: no warm-up at all.
+    // candidates, no resume.  warm == 2: the older flood + resume phases (kept for comparison): every
+    // epilogue group scans one tile and keeps everything, tc_threshold_kernel turns the union of all
+    // lists into the shared threshold, the same again after ~1/16 of the corpus, then the rest.
+    // warm == 0: local thresholds only.
     bool probed = false;
     if (warm == 1 && n_ctiles >= 8 * ngroups) {
         const int nlists = 2 * ngroups;
