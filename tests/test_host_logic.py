@@ -206,3 +206,23 @@ def test_sharded_search_gloo_world2(tmp_path, metric):
     port = _free_port()
     mp.spawn(_gloo_worker, args=(2, port, metric, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm: oracle.c on the host cores) keeps stdout to exactly one
+    JSON line carrying the contract's keys; nothing of archi_b200's CUDA path is needed for it."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = p.stdout.splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "queries_per_sec_exact_top10" and d["unit"] == "queries/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["rows"] == 1_000_000 and d["config"]["dim"] == 384 and d["config"]["k"] == 10
