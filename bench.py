@@ -261,7 +261,8 @@ def main():
     # least 2x the 126 MB L2 (strong scaling shrinks it), every timed step is followed by a flush
     # (a 256 MB memset) + synchronize, and the same loop with the flush alone is subtracted.
     L2_BYTES = 126e6
-    shard_read_bytes = cnt * dim * (2 if storage == "bf16" or os.environ.get("ARCHI_NO_SHADOW", "0") == "0" else 4)
+    # decided from the largest shard so that every rank takes the same branch (the flush loop holds a barrier)
+    shard_read_bytes = (-(-total_rows // world)) * dim * (2 if storage == "bf16" or os.environ.get("ARCHI_NO_SHADOW", "0") == "0" else 4)
     flush_l2 = shard_read_bytes < 2 * L2_BYTES
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_l2 else None
 
