@@ -226,3 +226,27 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["rows"] == 1_000_000 and d["config"]["dim"] == 384 and d["config"]["k"] == 10
+
+
+def test_probe_threshold_invariant():
+    """What the tensor path's probe launch relies on (csrc/tensor.cu, tc_maxima_threshold_kernel): the
+    k'-th largest of the per-32-column chunk maxima of ANY subset of the rows is a lower bound of the
+    k'-th largest key over all rows, because chunk maxima belong to distinct rows -- so no row of the
+    final top-k' can be rejected by it.  Masked rows (key -inf) only lower the bound."""
+    rng = np.random.default_rng(17)
+    for trial in range(20):
+        n, kprime = int(rng.integers(2000, 20000)), int(rng.choice([32, 64, 224]))
+        keys = rng.standard_normal(n).astype(np.float32)
+        if trial % 3 == 0:
+            keys[rng.random(n) < 0.3] = -np.inf                       # tombstones / filter
+        if trial % 4 == 0:
+            keys = np.round(keys, 1)                                   # heavy ties
+        probe = keys[: (n // 12) // 32 * 32].reshape(-1, 32)           # ~1/12 of the rows, whole chunks
+        maxima = probe.max(axis=1)
+        valid = maxima[maxima > -np.inf]
+        kth_all = np.sort(keys)[::-1][kprime - 1]
+        if valid.size >= kprime:
+            thr = np.sort(valid)[::-1][kprime - 1]
+            assert thr <= kth_all
+            # rows strictly above the threshold are what the main scan admits: at least ... the top ones
+            assert (keys > thr).sum() >= min(kprime - 1, (keys > kth_all).sum())
