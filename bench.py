@@ -333,7 +333,9 @@ def main():
                   "launch_ms": launch_ms, "algorithmic_bytes_per_launch": algo_bytes,
                   "algorithmic_flops_per_launch": algo_flops, "launches_per_step": st.passes, "grid": st.grid,
                   "achieved_GBps": gbs, "achieved_TFLOPs": tfs, "frac_hbm": gbs / peaks["hbm_gbs"],
-                  "frac_tensor_bf16_peak": tfs / peaks["bf16_tflops"], "unverified_queries": st.unverified_queries}
+                  "frac_tensor_bf16_peak": tfs / peaks["bf16_tflops"],
+                  "frac_tensor_bf16_sustained_peak": tfs / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                  "unverified_queries": st.unverified_queries}
         if t_tc >= t_hbm:
             note = " (kind::tf32 runs at half the bf16 rate; frac is against the bf16 peak)" if st.coarse_dtype != N.BF16 else ""
             return dict(common, bound="tensor", achieved=tfs, peak=peaks["bf16_tflops"], unit="TFLOP/s",
