@@ -9,7 +9,8 @@ from .vectorstore import B200VectorStore, Document
 from .retrievers import HybridRetriever, SemanticRetriever, GradingRetriever
 from .store import NativeStore, pool_normalize, merge_topk
 from .bm25 import LexicalIndex
-from .sharded import ShardedStore, plan_row_shards
+from .sharded import ShardedStore, PeerExchange, plan_row_shards
+from .ingest import IngestionDriver, IngestReport, split_text
 
 
 def __getattr__(name):
@@ -20,5 +21,5 @@ def __getattr__(name):
 
 
 __all__ = ["B200VectorStore", "Document", "HybridRetriever", "SemanticRetriever", "GradingRetriever",
-           "NativeStore", "pool_normalize", "merge_topk", "LexicalIndex", "ShardedStore",
-           "plan_row_shards", "B200Embeddings"]
+           "NativeStore", "pool_normalize", "merge_topk", "LexicalIndex", "ShardedStore", "PeerExchange",
+           "plan_row_shards", "IngestionDriver", "IngestReport", "split_text", "B200Embeddings"]

@@ -198,6 +198,62 @@ class B200VectorStore(_VectorStoreBase):
             coll.filter_cache.clear()
         return ids
 
+    def add_embedded_texts(self, texts: Iterable[str], embeddings: Any, metadatas: Optional[List[Dict[str, Any]]] = None,
+                           *, ids: Optional[List[str]] = None, document_id: Any = None) -> List[str]:
+        """Insert chunks whose embeddings already exist -- the VectorStoreManager path, which calls
+        ``embed_documents`` itself and then INSERTs (manager.py:373, 397-422).  ``embeddings``: [n, D] torch
+        CUDA tensor (stays on the device), numpy array or list of vectors, one per text.  Ids, metadata
+        stamping and the upsert on (document_id, chunk_index) are those of ``add_texts``."""
+        texts_list = list(texts)
+        if not texts_list:
+            return []
+        if ids is None:
+            ids = [str(uuid.uuid4()) for _ in texts_list]
+        if metadatas is None:
+            metadatas = [{} for _ in texts_list]
+        if len(metadatas) != len(texts_list) or len(ids) != len(texts_list):
+            raise ValueError("texts, metadatas and ids must have the same length")
+        if hasattr(embeddings, "is_cuda"):
+            emb = embeddings if embeddings.dim() == 2 else embeddings.reshape(len(texts_list), -1)
+            n_emb, dim = int(emb.shape[0]), int(emb.shape[1])
+        else:
+            emb = np.asarray(embeddings, dtype=np.float32)
+            if emb.ndim != 2:
+                raise ValueError("embeddings must be a [n, D] matrix")
+            n_emb, dim = emb.shape
+        if n_emb != len(texts_list):
+            raise ValueError("embeddings must hold one vector per text")
+        for meta in metadatas:
+            meta["collection"] = self._collection_name
+        coll = self._coll
+        with coll.lock:
+            replaced = []
+            if document_id is not None:
+                for i in range(len(texts_list)):
+                    old = coll.by_doc_chunk.get((document_id, i))
+                    if old is not None and coll.live[old]:
+                        replaced.append(old)
+            first = coll.ensure_native(dim).append(emb)
+            if replaced:
+                self._tombstone(replaced)
+            for i, (text, metadata, chunk_id) in enumerate(zip(texts_list, metadatas, ids)):
+                metadata["chunk_id"] = chunk_id
+                row = first + i
+                assert row == len(coll.texts)
+                coll.texts.append(text)
+                coll.metadatas.append(dict(metadata))
+                coll.document_ids.append(document_id)
+                coll.chunk_index.append(i)
+                coll.live.append(True)
+                coll.by_chunk_id.setdefault(chunk_id, []).append(row)
+                if document_id is not None:
+                    coll.by_doc_chunk[(document_id, i)] = row
+                    coll.by_document.setdefault(document_id, []).append(row)
+            if coll.lexical is not None:
+                coll.lexical.add_texts(texts_list)
+            coll.filter_cache.clear()
+        return ids
+
     def add_documents(self, documents: List[Document], **kwargs: Any) -> List[str]:
         """postgres_vectorstore.py:188-205."""
         texts = [doc.page_content for doc in documents]
