@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 import re
 from typing import Dict, List, Optional, Sequence
 
@@ -21,6 +22,7 @@ import numpy as np
 from . import _native as N
 
 _TOKEN_RE = re.compile(r"[a-z0-9]+")
+_NON_TOKEN_RE = re.compile(r"[^a-z0-9]+")
 
 
 def default_tokenize(text: str) -> List[str]:
@@ -28,43 +30,116 @@ def default_tokenize(text: str) -> List[str]:
     return _TOKEN_RE.findall(text.lower())
 
 
+# ---- host helper (archi_b200/hostsrc/text_index.c, plain C): tokenise + per-chunk term counts ------------
+_TEXT_LIB = None
+_TEXT_LIB_TRIED = False
+
+
+def _text_lib():
+    """libarchi_text.so, or None when it has not been built (the index then runs its Python path:
+    same postings, a dictionary instead of hashed term keys)."""
+    global _TEXT_LIB, _TEXT_LIB_TRIED
+    if not _TEXT_LIB_TRIED:
+        _TEXT_LIB_TRIED = True
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libarchi_text.so")
+        if os.path.exists(path):
+            try:
+                lib = ctypes.CDLL(path)
+                lib.archi_text_index_batch.restype = ctypes.c_int64
+                lib.archi_text_index_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                       ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+                lib.archi_text_term_key.restype = ctypes.c_uint64
+                lib.archi_text_term_key.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+                _TEXT_LIB = lib
+            except OSError:
+                _TEXT_LIB = None
+    return _TEXT_LIB
+
+
 class LexicalIndex:
+    """Chunks are kept as (term key, term frequency) pairs.  With the default tokenizer and the host
+    helper built, a term key is the 64-bit FNV-1a hash of the token and a whole batch of chunks is
+    tokenised and counted in one C call; otherwise (custom ``tokenize``, or integer term ids given
+    directly) keys come from a Python dictionary / the ids themselves.  Term ids -- positions in the
+    sorted array of distinct keys -- only exist after ``_rebuild``."""
+
     def __init__(self, device: int = 0, k1: float = 1.2, b: float = 0.75, sign: float = 1.0, tokenize=default_tokenize):
         self.device, self.k1, self.b, self.sign, self.tokenize = int(device), float(k1), float(b), float(sign), tokenize
-        self._vocab: Dict[str, int] = {}
-        self._doc_terms: List[np.ndarray] = []   # per row: sorted unique term ids
-        self._doc_tfs: List[np.ndarray] = []     # per row: term frequencies
-        self._doc_len: List[int] = []
+        self._fast = tokenize is default_tokenize and _text_lib() is not None
+        self._vocab: Dict[str, int] = {}         # Python path only: token -> key
+        # per added batch: keys uint64 [pairs], tfs int32 [pairs], pairs per chunk int64 [docs], tokens per chunk int32 [docs]
+        self._batches: List[tuple] = []
+        self._n_docs = 0
         self._deleted: set = set()
         self._dirty = True
         # device CSR (built lazily)
         self._post_ptr: Optional[np.ndarray] = None
         self._doc_ids_dev = self._tfs_dev = self._doc_len_dev = None
         self._df: Optional[np.ndarray] = None
+        self._term_keys = np.empty(0, dtype=np.uint64)
         self._n_live = 0
         self._avgdl = 1.0
 
     def __len__(self) -> int:
-        return len(self._doc_len)
+        return self._n_docs
 
     # ---- building ------------------------------------------------------------------------------
     def add_texts(self, texts: Sequence[str]) -> None:
+        texts = list(texts)
+        if not texts:
+            return
+        if self._fast:
+            self._add_texts_fast(texts)
+            return
+        docs = []
         for t in texts:
             ids = [self._vocab.setdefault(tok, len(self._vocab)) for tok in self.tokenize(t)]
-            self.add_token_ids(np.asarray(ids, dtype=np.int64))
+            docs.append(np.asarray(ids, dtype=np.int64))
+        self._add_id_docs(docs)
+
+    def _add_texts_fast(self, texts: List[str]) -> None:
+        # non-ASCII chunks are lower-cased by Python (Unicode rules) and reduced to ASCII tokens first;
+        # ASCII chunks go to the helper untouched (it lower-cases A-Z itself)
+        blobs = [(t if t.isascii() else _NON_TOKEN_RE.sub(" ", t.lower())).encode("ascii") for t in texts]
+        n = len(blobs)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.fromiter(map(len, blobs), dtype=np.int64, count=n), out=offs[1:])
+        text = b"".join(blobs)
+        cap = int(offs[-1]) // 2 + n + 1                      # a token needs a byte and a separator
+        keys = np.empty(cap, dtype=np.uint64)
+        tfs = np.empty(cap, dtype=np.int32)
+        doc_ptr = np.empty(n + 1, dtype=np.int64)
+        doc_len = np.empty(n, dtype=np.int32)
+        w = _text_lib().archi_text_index_batch(text, offs.ctypes.data, n, keys.ctypes.data, tfs.ctypes.data, cap,
+                                               doc_ptr.ctypes.data, doc_len.ctypes.data)
+        if w < 0:
+            raise RuntimeError(f"archi_text_index_batch failed with code {w}")
+        self._batches.append((keys[:w].copy(), tfs[:w].copy(), np.diff(doc_ptr), doc_len))
+        self._n_docs += n
+        self._dirty = True
+
+    def _add_id_docs(self, docs: List[np.ndarray]) -> None:
+        """Chunks given as arrays of non-negative integer term keys (one entry per token occurrence)."""
+        keys, tfs, counts, lens = [], [], [], []
+        for ids in docs:
+            terms, tf = np.unique(np.asarray(ids, dtype=np.int64), return_counts=True)
+            keys.append(terms.astype(np.uint64))
+            tfs.append(tf.astype(np.int32))
+            counts.append(terms.size)
+            lens.append(int(np.asarray(ids).size))
+        self._batches.append((np.concatenate(keys) if keys else np.empty(0, np.uint64),
+                              np.concatenate(tfs) if tfs else np.empty(0, np.int32),
+                              np.asarray(counts, dtype=np.int64), np.asarray(lens, dtype=np.int32)))
+        self._n_docs += len(docs)
+        self._dirty = True
 
     def add_token_ids(self, token_ids: np.ndarray) -> None:
         """One document given as an array of integer term ids (synthetic corpora skip tokenising)."""
-        terms, tfs = np.unique(np.asarray(token_ids, dtype=np.int64), return_counts=True)
-        self._doc_terms.append(terms)
-        self._doc_tfs.append(tfs.astype(np.int32))
-        self._doc_len.append(int(token_ids.size))
-        self._dirty = True
+        self._add_id_docs([np.asarray(token_ids, dtype=np.int64)])
 
     def add_token_matrix(self, tokens: np.ndarray) -> None:
-        """[n_docs, doc_len] integer term ids, vectorised."""
-        for row in np.asarray(tokens):
-            self.add_token_ids(row)
+        """[n_docs, doc_len] integer term ids."""
+        self._add_id_docs([row for row in np.asarray(tokens)])
 
     def delete_rows(self, rows) -> None:
         self._deleted.update(int(r) for r in rows)
@@ -73,40 +148,65 @@ class LexicalIndex:
     def reset(self) -> None:
         self.__init__(self.device, self.k1, self.b, self.sign, self.tokenize)
 
-    def _rebuild(self) -> None:
-        import torch
-        n = len(self._doc_len)
+    def _host_csr(self):
+        """Posting lists on the host: (term_keys sorted uint64 [T], df int64 [T], post_ptr int64 [T+1],
+        doc_ids int32 [P] grouped by term and ascending inside a term, tfs int32 [P], doc_len float32
+        [docs], n_live, avgdl).  Deleted chunks keep their row but have no postings."""
+        n = self._n_docs
         live = np.ones(n, dtype=bool)
         if self._deleted:
             live[np.fromiter(self._deleted, dtype=np.int64)] = False
-        if n:
-            lens = np.asarray([t.size for t in self._doc_terms], dtype=np.int64)
-            doc_of = np.repeat(np.arange(n, dtype=np.int64), lens)
-            terms = np.concatenate(self._doc_terms) if lens.sum() else np.empty(0, np.int64)
-            tfs = np.concatenate(self._doc_tfs) if lens.sum() else np.empty(0, np.int32)
-            keep = live[doc_of]
-            doc_of, terms, tfs = doc_of[keep], terms[keep], tfs[keep]
+        if self._batches:
+            keys = np.concatenate([b[0] for b in self._batches])
+            tfs = np.concatenate([b[1] for b in self._batches])
+            counts = np.concatenate([b[2] for b in self._batches])
+            dl = np.concatenate([b[3] for b in self._batches]).astype(np.float32)
         else:
-            doc_of, terms, tfs = np.empty(0, np.int64), np.empty(0, np.int64), np.empty(0, np.int32)
-        n_terms = int(terms.max()) + 1 if terms.size else 0
+            keys, tfs = np.empty(0, np.uint64), np.empty(0, np.int32)
+            counts, dl = np.empty(0, np.int64), np.empty(0, np.float32)
+        doc_of = np.repeat(np.arange(n, dtype=np.int64), counts)
+        keep = live[doc_of]
+        doc_of, keys, tfs = doc_of[keep], keys[keep], tfs[keep]
+        term_keys, terms = np.unique(keys, return_inverse=True)
         order = np.lexsort((doc_of, terms))
         terms, doc_of, tfs = terms[order], doc_of[order], tfs[order]
-        self._df = np.bincount(terms, minlength=n_terms).astype(np.int64)
-        self._post_ptr = np.concatenate([[0], np.cumsum(self._df)]).astype(np.int64)
-        dl = np.asarray(self._doc_len, dtype=np.float32)
-        self._n_live = int(live.sum())
-        self._avgdl = float(dl[live].mean()) if self._n_live and dl[live].sum() > 0 else 1.0
+        df = np.bincount(terms, minlength=term_keys.size).astype(np.int64)
+        post_ptr = np.concatenate([[0], np.cumsum(df)]).astype(np.int64)
+        n_live = int(live.sum())
+        avgdl = float(dl[live].mean()) if n_live and dl[live].sum() > 0 else 1.0
+        return term_keys, df, post_ptr, doc_of.astype(np.int32), tfs.astype(np.int32), dl, n_live, avgdl
+
+    def _rebuild(self) -> None:
+        import torch
+        self._term_keys, self._df, self._post_ptr, doc_ids, tfs, dl, self._n_live, self._avgdl = self._host_csr()
         dev = torch.device("cuda", self.device)
-        self._doc_ids_dev = torch.from_numpy(doc_of.astype(np.int32)).to(dev)
-        self._tfs_dev = torch.from_numpy(tfs.astype(np.int32)).to(dev)
+        self._doc_ids_dev = torch.from_numpy(doc_ids).to(dev)
+        self._tfs_dev = torch.from_numpy(tfs).to(dev)
         self._doc_len_dev = torch.from_numpy(dl).to(dev)
         self._dirty = False
 
     # ---- scoring -------------------------------------------------------------------------------
-    def query_terms(self, query) -> List[int]:
+    def _query_keys(self, query) -> np.ndarray:
+        """Term keys of the query, one per token occurrence, in query order."""
         if isinstance(query, str):
-            return [self._vocab[t] for t in self.tokenize(query) if t in self._vocab]
-        return [int(t) for t in np.asarray(query).reshape(-1)]
+            if self._fast:
+                lib = _text_lib()
+                toks = [t.encode("ascii") for t in default_tokenize(query)]
+                return np.asarray([lib.archi_text_term_key(t, len(t)) for t in toks], dtype=np.uint64)
+            known = [self._vocab[t] for t in self.tokenize(query) if t in self._vocab]
+            return np.asarray(known, dtype=np.uint64)
+        return np.asarray(query).reshape(-1).astype(np.int64).astype(np.uint64)
+
+    def query_terms(self, query) -> List[int]:
+        """Term ids (positions in the sorted key array of the last rebuild) of the query's tokens that
+        occur in the index; repeated tokens are kept."""
+        keys = self._query_keys(query)
+        if keys.size == 0 or self._term_keys.size == 0:
+            return []
+        idx = np.searchsorted(self._term_keys, keys)
+        idx[idx >= self._term_keys.size] = 0
+        hit = self._term_keys[idx] == keys
+        return [int(t) for t in idx[hit]]
 
     def idf(self, term: int) -> float:
         df = int(self._df[term]) if 0 <= term < self._df.size else 0
@@ -117,7 +217,7 @@ class LexicalIndex:
         import torch
         if self._dirty:
             self._rebuild()
-        n = len(self._doc_len)
+        n = self._n_docs
         dev = torch.device("cuda", self.device)
         if out is None:
             out = torch.zeros(n, dtype=torch.float32, device=dev)

@@ -1,4 +1,5 @@
-"""Builds archi_b200/lib/libarchi_b200.so in-tree with nvcc for sm_100a (no other target).
+"""Builds archi_b200/lib/libarchi_b200.so in-tree with nvcc for sm_100a (no other target), and the
+small host-only helper archi_b200/lib/libarchi_text.so (gcc; tokenising for the lexical index).
 
 ``python -m archi_b200.build [--force] [--verbose]``; also called by ``__graft_entry__.build()``.
 The built .so is git-ignored but travels to the GPU box with the gpurun snapshot.
@@ -17,6 +18,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libarchi_b200.so")
+HOSTSRC = os.path.join(HERE, "hostsrc")
+TEXT_LIB = os.path.join(LIBDIR, "libarchi_text.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -48,7 +51,24 @@ def is_stale() -> bool:
     return not os.path.exists(LIB) or os.path.getmtime(LIB) < _deps_mtime()
 
 
+def build_host(force: bool = False) -> str:
+    """libarchi_text.so: plain C, no CUDA (archi_b200/hostsrc/text_index.c)."""
+    src = os.path.join(HOSTSRC, "text_index.c")
+    if not force and os.path.exists(TEXT_LIB) and os.path.getmtime(TEXT_LIB) >= os.path.getmtime(src):
+        return TEXT_LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        raise RuntimeError("gcc not found; libarchi_text.so cannot be built")
+    res = subprocess.run([gcc, "-O2", "-shared", "-fPIC", "-o", TEXT_LIB, src], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("building libarchi_text.so failed")
+    return TEXT_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_host(force)
     if not force and not is_stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
