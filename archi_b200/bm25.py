@@ -138,8 +138,24 @@ class LexicalIndex:
         self._add_id_docs([np.asarray(token_ids, dtype=np.int64)])
 
     def add_token_matrix(self, tokens: np.ndarray) -> None:
-        """[n_docs, doc_len] integer term ids."""
-        self._add_id_docs([row for row in np.asarray(tokens)])
+        """[n_docs, doc_len] integer term ids, reduced to (term, frequency) pairs in one vectorised pass."""
+        t = np.sort(np.asarray(tokens, dtype=np.int64), axis=1)
+        if t.ndim != 2:
+            raise ValueError("tokens must be a [n_docs, doc_len] matrix")
+        n, length = t.shape
+        if n == 0:
+            return
+        if length == 0:
+            self._add_id_docs([np.empty(0, np.int64)] * n)
+            return
+        start = np.ones(t.shape, dtype=bool)                  # first occurrence of a term in its (sorted) row
+        start[:, 1:] = t[:, 1:] != t[:, :-1]
+        at = np.flatnonzero(start.ravel())
+        tfs = np.diff(np.append(at, t.size)).astype(np.int32)  # a run never crosses a row: every row starts one
+        self._batches.append((t[start].astype(np.uint64), tfs, start.sum(axis=1).astype(np.int64),
+                              np.full(n, length, dtype=np.int32)))
+        self._n_docs += n
+        self._dirty = True
 
     def delete_rows(self, rows) -> None:
         self._deleted.update(int(r) for r in rows)
