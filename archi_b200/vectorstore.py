@@ -67,7 +67,11 @@ class _Collection:
         self.by_document: Dict[Any, List[int]] = {}
         self.documents: Dict[Any, Dict[str, Any]] = {}  # document-level metadata + is_deleted
         self.lexical: Optional[LexicalIndex] = LexicalIndex(device) if bm25_index else None
-        self.filter_cache: Dict[str, Dict[str, np.ndarray]] = {}
+        # metadata equality filters: per key, value text -> row ids, extended incrementally as rows are added
+        self.filter_index: Dict[str, Dict[str, Any]] = {}
+        # packed device bitmasks per (filter, include_deleted), valid for (rows, docs_epoch)
+        self.mask_cache: Dict[Tuple, Tuple[int, int, Any]] = {}
+        self.docs_epoch = 0             # bumped when a document's is_deleted flag changes
         self.lock = threading.RLock()
 
     def ensure_native(self, dim: int) -> NativeStore:
@@ -143,6 +147,8 @@ class B200VectorStore(_VectorStoreBase):
         with self._coll.lock:
             rec = self._coll.documents.setdefault(document_id, {})
             rec.update({k: v for k, v in fields.items() if k in _DOC_FIELDS})
+            if rec.get("is_deleted", False) != bool(is_deleted):
+                self._coll.docs_epoch += 1
             rec["is_deleted"] = bool(is_deleted)
 
     # ---- add ------------------------------------------------------------------------------------------
@@ -159,25 +165,34 @@ class B200VectorStore(_VectorStoreBase):
         for meta in metadatas:
             meta["collection"] = self._collection_name
         document_id = kwargs.get("document_id")
-        coll = self._coll
         ef = self._embedding_function
+
+        def embed_and_append(coll):
+            if hasattr(ef, "embed_documents_into"):
+                # B200Embeddings: encoder forward -> fused pool+normalise kernel writes the rows
+                return ef.embed_documents_into(texts_list, coll)
+            embeddings = ef.embed_documents(texts_list)
+            arr = np.asarray(embeddings, dtype=np.float32)
+            if arr.ndim != 2 or arr.shape[0] != len(texts_list):
+                raise ValueError("embed_documents must return one vector per text")
+            return coll.ensure_native(arr.shape[1]).append(arr)
+
+        return self._insert_rows(texts_list, metadatas, ids, document_id, embed_and_append)
+
+    def _insert_rows(self, texts_list: List[str], metadatas: List[Dict[str, Any]], ids: List[str], document_id: Any,
+                     append_rows) -> List[str]:
+        """Bookkeeping shared by add_texts / add_embedded_texts: upsert on (document_id, chunk_index) -- the
+        replaced rows become tombstones (:173-176) --, chunk_id stamping (:157), host-side text / metadata /
+        lexical index.  ``append_rows(coll)`` puts the embeddings into the native store and returns the first row."""
+        coll = self._coll
         with coll.lock:
-            # upsert on (document_id, chunk_index): the replaced rows become tombstones (:173-176)
             replaced = []
             if document_id is not None:
                 for i in range(len(texts_list)):
                     old = coll.by_doc_chunk.get((document_id, i))
                     if old is not None and coll.live[old]:
                         replaced.append(old)
-            if hasattr(ef, "embed_documents_into"):
-                # B200Embeddings: encoder forward -> fused pool+normalise kernel writes the rows
-                first = ef.embed_documents_into(texts_list, coll)
-            else:
-                embeddings = ef.embed_documents(texts_list)
-                arr = np.asarray(embeddings, dtype=np.float32)
-                if arr.ndim != 2 or arr.shape[0] != len(texts_list):
-                    raise ValueError("embed_documents must return one vector per text")
-                first = coll.ensure_native(arr.shape[1]).append(arr)
+            first = append_rows(coll)
             if replaced:
                 self._tombstone(replaced)
             for i, (text, metadata, chunk_id) in enumerate(zip(texts_list, metadatas, ids)):
@@ -195,7 +210,6 @@ class B200VectorStore(_VectorStoreBase):
                     coll.by_document.setdefault(document_id, []).append(row)
             if coll.lexical is not None:
                 coll.lexical.add_texts(texts_list)
-            coll.filter_cache.clear()
         return ids
 
     def add_embedded_texts(self, texts: Iterable[str], embeddings: Any, metadatas: Optional[List[Dict[str, Any]]] = None,
@@ -225,34 +239,7 @@ class B200VectorStore(_VectorStoreBase):
             raise ValueError("embeddings must hold one vector per text")
         for meta in metadatas:
             meta["collection"] = self._collection_name
-        coll = self._coll
-        with coll.lock:
-            replaced = []
-            if document_id is not None:
-                for i in range(len(texts_list)):
-                    old = coll.by_doc_chunk.get((document_id, i))
-                    if old is not None and coll.live[old]:
-                        replaced.append(old)
-            first = coll.ensure_native(dim).append(emb)
-            if replaced:
-                self._tombstone(replaced)
-            for i, (text, metadata, chunk_id) in enumerate(zip(texts_list, metadatas, ids)):
-                metadata["chunk_id"] = chunk_id
-                row = first + i
-                assert row == len(coll.texts)
-                coll.texts.append(text)
-                coll.metadatas.append(dict(metadata))
-                coll.document_ids.append(document_id)
-                coll.chunk_index.append(i)
-                coll.live.append(True)
-                coll.by_chunk_id.setdefault(chunk_id, []).append(row)
-                if document_id is not None:
-                    coll.by_doc_chunk[(document_id, i)] = row
-                    coll.by_document.setdefault(document_id, []).append(row)
-            if coll.lexical is not None:
-                coll.lexical.add_texts(texts_list)
-            coll.filter_cache.clear()
-        return ids
+        return self._insert_rows(texts_list, metadatas, ids, document_id, lambda coll: coll.ensure_native(dim).append(emb))
 
     def add_documents(self, documents: List[Document], **kwargs: Any) -> List[str]:
         """postgres_vectorstore.py:188-205."""
@@ -356,44 +343,58 @@ class B200VectorStore(_VectorStoreBase):
             coll.live[r] = False
         if coll.lexical is not None:
             coll.lexical.delete_rows(rows)
-        coll.filter_cache.clear()
+
+    def _filter_rows(self, key: str, value_text: str) -> List[int]:
+        """Row ids whose ``metadata->>key`` equals ``value_text``.  The per-key index is built in one pass
+        over the rows and extended in place as rows are added (never rebuilt, never per distinct value)."""
+        coll = self._coll
+        n = len(coll.metadatas)
+        index = coll.filter_index.get(key)
+        if index is None:
+            index = coll.filter_index[key] = {"n": 0, "rows": {}}
+        if index["n"] < n:
+            rows = index["rows"]
+            for r in range(index["n"], n):
+                v = coll.metadatas[r].get(key)
+                if v is not None:
+                    rows.setdefault(_json_text(v), []).append(r)
+            index["n"] = n
+        return index["rows"].get(value_text, [])
 
     def _where_mask(self, metadata_filter: Dict[str, Any], include_deleted: bool):
         """The WHERE clause (:296-310) as a device bitmask, or None when every row passes.
         ``metadata->>'key' = str(value)`` per filter key; documents flagged is_deleted are excluded
-        unless include_deleted.  (Rows removed with delete() are tombstoned in the native store.)"""
+        unless include_deleted.  (Rows removed with delete() are tombstoned in the native store.)
+        The packed mask stays on the device, keyed by (filter, include_deleted), until rows are added or a
+        document's is_deleted flag changes."""
         coll = self._coll
         n = len(coll.texts)
+        gone = [] if include_deleted else [d for d, rec in coll.documents.items() if rec.get("is_deleted")]
+        if not metadata_filter and not gone:
+            return None
+        cache_key = (tuple(sorted((str(k), str(v)) for k, v in metadata_filter.items())), bool(include_deleted))
+        hit = coll.mask_cache.get(cache_key)
+        if hit is not None and hit[0] == n and hit[1] == coll.docs_epoch:
+            return hit[2]
         keep: Optional[np.ndarray] = None
         for key, value in metadata_filter.items():
-            index = coll.filter_cache.get(key)
-            if index is None:
-                index = {}
-                vals = np.asarray(["\0" if key not in m or m[key] is None else _json_text(m[key])
-                                   for m in coll.metadatas], dtype=object)
-                for v in set(vals.tolist()):
-                    if v != "\0":
-                        index[v] = np.nonzero(vals == v)[0]
-                coll.filter_cache[key] = index
-            rows = index.get(str(value), np.empty(0, dtype=np.int64))
             sel = np.zeros(n, dtype=bool)
-            sel[rows] = True
+            sel[np.asarray(self._filter_rows(key, str(value)), dtype=np.int64)] = True
             keep = sel if keep is None else (keep & sel)
-        if not include_deleted:
-            gone = [d for d, rec in coll.documents.items() if rec.get("is_deleted")]
-            if gone:
-                sel = np.ones(n, dtype=bool)
-                for d in gone:
-                    sel[coll.by_document.get(d, [])] = False
-                keep = sel if keep is None else (keep & sel)
-        if keep is None:
-            return None
-        import torch
+        if gone:
+            sel = np.ones(n, dtype=bool)
+            for d in gone:
+                sel[np.asarray(coll.by_document.get(d, []), dtype=np.int64)] = False
+            keep = sel if keep is None else (keep & sel)
         pad = (-n) % 32
         bits = np.concatenate([keep, np.zeros(pad, dtype=bool)]) if pad else keep
         words = np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
         words = np.concatenate([words, np.zeros(1, dtype=np.uint32)])
-        return torch.from_numpy(words.view(np.int32).copy()).to(torch.device("cuda", coll.device))
+        mask = _upload_mask_words(words, coll.device)
+        if len(coll.mask_cache) >= 64:
+            coll.mask_cache.clear()
+        coll.mask_cache[cache_key] = (n, coll.docs_epoch, mask)
+        return mask
 
     def _rows_to_results(self, ids: np.ndarray, scores: np.ndarray) -> List[Tuple[Document, float]]:
         coll = self._coll
@@ -409,6 +410,12 @@ class B200VectorStore(_VectorStoreBase):
                         metadata[f] = rec[f]
             results.append((Document(page_content=coll.texts[row], metadata=metadata), float(score)))
         return results
+
+
+def _upload_mask_words(words: np.ndarray, device: int):
+    """uint32 bitmask words -> int32 CUDA tensor on the collection's GPU."""
+    import torch
+    return torch.from_numpy(words.view(np.int32).copy()).to(torch.device("cuda", device))
 
 
 def _json_text(v: Any) -> str:

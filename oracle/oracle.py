@@ -87,7 +87,16 @@ def topk_from_keys(keys: np.ndarray, k: int, ascending: bool = True) -> Tuple[np
     n = keys.shape[1]
     kk = min(k, n)
     order_keys = keys if ascending else -keys
-    idx = np.argsort(order_keys, axis=1, kind="stable")[:, :kk]
+    if kk > 0 and n > 16 * kk and not np.isnan(order_keys).any():
+        # same result as the full stable sort, without sorting N keys per query: everything up to the
+        # kk-th smallest key (ties included) is a candidate, candidates are visited in id order
+        kth = np.partition(order_keys, kk - 1, axis=1)[:, kk - 1]
+        idx = np.empty((keys.shape[0], kk), dtype=np.int64)
+        for r in range(keys.shape[0]):
+            cand = np.flatnonzero(order_keys[r] <= kth[r])
+            idx[r] = cand[np.argsort(order_keys[r, cand], kind="stable")[:kk]]
+    else:
+        idx = np.argsort(order_keys, axis=1, kind="stable")[:, :kk]
     vals = np.take_along_axis(keys, idx, axis=1)
     return vals, idx.astype(np.int64)
 
@@ -157,6 +166,58 @@ def same_topk_up_to_ties(ids_a: Sequence[int], ids_b: Sequence[int], keys_b: Seq
     tol = abs_tol + rel_tol * abs(kth)
     strict = {i for i, s in zip(b, keys_b) if abs(float(s) - kth) > tol}
     return strict.issubset(set(a))
+
+
+def pair_distances_f64(metric: str, rows: np.ndarray, query: np.ndarray) -> np.ndarray:
+    """fp64 distances of ONE query to a handful of gathered rows [m, D] (same definitions as distances_f64)."""
+    if rows.shape[0] == 0:
+        return np.empty(0)
+    d = distances_f64(metric, rows, query)[0]
+    return np.where(np.isnan(d), np.inf, d)
+
+
+def verify_topk(metric: str, stored: np.ndarray, queries: np.ndarray, k: int, ids: np.ndarray, scores: np.ndarray,
+                rel: float, d_true: np.ndarray, i_true: np.ndarray, mask: Optional[np.ndarray] = None,
+                id_tol_rel: float = 2e-6, id_tol_abs: float = 1e-7) -> List[str]:
+    """Tie-aware and exact comparison of a returned top-k with the fp64 truth (d_true, i_true of exact_topk or
+    oracle.c on the same stored values).  Unlike ``same_topk_up_to_ties`` every returned id is re-scored in
+    fp64 from ``stored``, so an id outside the truth list is accepted only if its own distance ties the k-th
+    truth distance.  Returns a list of failure descriptions (empty = pass).  Per query:
+      * min(k, rows passing) distinct ids, all passing ``mask``; the tail is id -1 / score NaN;
+      * every truth id strictly better than the k-th truth distance (beyond the tie tolerance) is returned;
+      * every returned id's fp64 distance is <= the k-th truth distance + tolerance;
+      * returned scores, rank by rank, within ``rel`` of the truth scores and best first."""
+    fails: List[str] = []
+    queries = np.atleast_2d(queries)
+    s_true = score_from_distance(metric, d_true)
+    kk = d_true.shape[1]
+    for q in range(queries.shape[0]):
+        got = [int(x) for x in ids[q, :kk]]
+        if len(set(got)) != kk or min(got, default=0) < 0:
+            fails.append(f"q{q}: ids not distinct/valid {got}")
+            continue
+        if not ((ids[q, kk:] == -1).all() and np.isnan(scores[q, kk:]).all()):
+            fails.append(f"q{q}: tail not empty")
+        if mask is not None and not np.asarray(mask)[got].all():
+            fails.append(f"q{q}: returned a masked row")
+        if kk == 0:
+            continue
+        kth = float(d_true[q, -1])
+        tol = id_tol_abs + id_tol_rel * abs(kth)
+        strict = {int(i) for i, d in zip(i_true[q], d_true[q]) if d < kth - tol}
+        if not strict.issubset(got):
+            fails.append(f"q{q}: missing strictly-better ids {sorted(strict - set(got))}")
+        extra = [i for i in got if i not in set(int(x) for x in i_true[q])]
+        if extra:
+            d_extra = pair_distances_f64(metric, np.asarray(stored[extra], dtype=np.float64), queries[q])
+            if (d_extra > kth + tol).any():
+                fails.append(f"q{q}: ids {extra} are not ties of the k-th distance {kth}: {d_extra.tolist()}")
+        if not np.allclose(scores[q, :kk], s_true[q], rtol=rel, atol=rel * 1e-1):
+            fails.append(f"q{q}: scores {scores[q, :kk].tolist()} vs {s_true[q].tolist()}")
+        key = scores[q, :kk] if metric == "cosine" else -scores[q, :kk]
+        if not (np.diff(key) <= 1e-7).all():
+            fails.append(f"q{q}: not best first")
+    return fails
 
 
 # --------------------------------------------------------------------------------------------
