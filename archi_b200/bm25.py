@@ -56,6 +56,34 @@ def _text_lib():
     return _TEXT_LIB
 
 
+class TableStats:
+    """Corpus statistics of one ``document_chunks`` table.  The reference's BM25 index is built on the table
+    (init.sql:297-300), so N, df and avgdl come from the chunks of EVERY collection stored in it, while a
+    search only returns the rows of one collection (postgres_vectorstore.py:420-430).  Each collection keeps
+    its own posting lists (LexicalIndex); the indexes of one database share one TableStats."""
+
+    def __init__(self):
+        self.members: List["LexicalIndex"] = []
+
+    def refresh(self) -> None:
+        for m in self.members:
+            if m._dirty:
+                m._rebuild()
+
+    def n_live(self) -> int:
+        return sum(m._n_live for m in self.members)
+
+    def avgdl(self) -> float:
+        n, total = self.n_live(), sum(m._sum_dl for m in self.members)
+        return float(total / n) if n and total > 0 else 1.0
+
+    def df_of_keys(self, keys: np.ndarray) -> np.ndarray:
+        out = np.zeros(keys.size, dtype=np.int64)
+        for m in self.members:
+            out += m._df_of_keys(keys)
+        return out
+
+
 class LexicalIndex:
     """Chunks are kept as (term key, term frequency) pairs.  With the default tokenizer and the host
     helper built, a term key is the 64-bit FNV-1a hash of the token and a whole batch of chunks is
@@ -63,8 +91,13 @@ class LexicalIndex:
     directly) keys come from a Python dictionary / the ids themselves.  Term ids -- positions in the
     sorted array of distinct keys -- only exist after ``_rebuild``."""
 
-    def __init__(self, device: int = 0, k1: float = 1.2, b: float = 0.75, sign: float = 1.0, tokenize=default_tokenize):
+    def __init__(self, device: int = 0, k1: float = 1.2, b: float = 0.75, sign: float = 1.0, tokenize=default_tokenize,
+                 table: Optional[TableStats] = None):
         self.device, self.k1, self.b, self.sign, self.tokenize = int(device), float(k1), float(b), float(sign), tokenize
+        self.table = table if table is not None else TableStats()
+        if self not in self.table.members:
+            self.table.members.append(self)
+        self._sum_dl = 0.0
         self._fast = tokenize is default_tokenize and _text_lib() is not None
         self._vocab: Dict[str, int] = {}         # Python path only: token -> key
         # per added batch: keys uint64 [pairs], tfs int32 [pairs], pairs per chunk int64 [docs], tokens per chunk int32 [docs]
@@ -162,7 +195,20 @@ class LexicalIndex:
         self._dirty = True
 
     def reset(self) -> None:
-        self.__init__(self.device, self.k1, self.b, self.sign, self.tokenize)
+        self.__init__(self.device, self.k1, self.b, self.sign, self.tokenize, self.table)
+
+    def detach(self) -> None:
+        """Leave the table statistics (the collection is dropped)."""
+        if self in self.table.members:
+            self.table.members.remove(self)
+
+    def _df_of_keys(self, keys: np.ndarray) -> np.ndarray:
+        """Document frequency, in THIS index, of each term key (0 for unknown keys)."""
+        if self._df is None or self._term_keys.size == 0 or keys.size == 0:
+            return np.zeros(keys.size, dtype=np.int64)
+        idx = np.searchsorted(self._term_keys, keys)
+        idx[idx >= self._term_keys.size] = 0
+        return np.where(self._term_keys[idx] == keys, self._df[idx], 0).astype(np.int64)
 
     def _host_csr(self):
         """Posting lists on the host: (term_keys sorted uint64 [T], df int64 [T], post_ptr int64 [T+1],
@@ -189,6 +235,7 @@ class LexicalIndex:
         df = np.bincount(terms, minlength=term_keys.size).astype(np.int64)
         post_ptr = np.concatenate([[0], np.cumsum(df)]).astype(np.int64)
         n_live = int(live.sum())
+        self._sum_dl = float(dl[live].sum()) if n_live else 0.0
         avgdl = float(dl[live].mean()) if n_live and dl[live].sum() > 0 else 1.0
         return term_keys, df, post_ptr, doc_of.astype(np.int32), tfs.astype(np.int32), dl, n_live, avgdl
 
@@ -225,12 +272,23 @@ class LexicalIndex:
         return [int(t) for t in idx[hit]]
 
     def idf(self, term: int) -> float:
-        df = int(self._df[term]) if 0 <= term < self._df.size else 0
-        return math.log(1.0 + (self._n_live - df + 0.5) / (df + 0.5))
+        """idf of a term of this index over the whole table (every index sharing ``self.table``)."""
+        if not (0 <= term < self._df.size):
+            df = 0
+        elif len(self.table.members) == 1:
+            df = int(self._df[term])
+        else:
+            df = int(self.table.df_of_keys(self._term_keys[term:term + 1])[0])
+        n = self.table.n_live() if len(self.table.members) > 1 else self._n_live
+        return math.log(1.0 + (n - df + 0.5) / (df + 0.5))
+
+    def avgdl(self) -> float:
+        return self.table.avgdl() if len(self.table.members) > 1 else self._avgdl
 
     def score(self, query, out=None):
         """Dense fp32 [rows] BM25 scores of ``query`` on the GPU, 0 where no term matches."""
         import torch
+        self.table.refresh()
         if self._dirty:
             self._rebuild()
         n = self._n_docs
@@ -251,5 +309,5 @@ class LexicalIndex:
             starts.ctypes.data_as(ctypes.c_void_p), ends.ctypes.data_as(ctypes.c_void_p), len(terms),
             idf.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(self._doc_ids_dev.data_ptr()),
             ctypes.c_void_p(self._tfs_dev.data_ptr()), ctypes.c_void_p(self._doc_len_dev.data_ptr()),
-            self._avgdl, self.k1, self.b, self.sign, ctypes.c_void_p(out.data_ptr()), stream))
+            self.avgdl(), self.k1, self.b, self.sign, ctypes.c_void_p(out.data_ptr()), stream))
         return out

@@ -15,13 +15,14 @@ Differences that a maintainer should know (all deliberate):
 """
 from __future__ import annotations
 
+import json
 import threading
 import uuid
 from typing import Any, Dict, Iterable, List, Optional, Tuple, Type
 
 import numpy as np
 
-from .bm25 import LexicalIndex
+from .bm25 import LexicalIndex, TableStats
 from .store import NativeStore
 
 try:  # the reference subclasses langchain_core's VectorStore (postgres_vectorstore.py:16-18)
@@ -54,7 +55,8 @@ _DOC_FIELDS = ("resource_hash", "display_name", "source_type", "url")    # postg
 class _Collection:
     """GPU-resident state of one collection, shared by every store object that names it."""
 
-    def __init__(self, name: str, metric: str, device: int, storage_dtype: str, bm25_index: bool):
+    def __init__(self, name: str, metric: str, device: int, storage_dtype: str, bm25_index: bool,
+                 table: Optional[TableStats] = None):
         self.name, self.metric, self.device, self.storage_dtype = name, metric, device, storage_dtype
         self.native: Optional[NativeStore] = None
         self.texts: List[str] = []
@@ -66,7 +68,7 @@ class _Collection:
         self.by_doc_chunk: Dict[Tuple[Any, int], int] = {}
         self.by_document: Dict[Any, List[int]] = {}
         self.documents: Dict[Any, Dict[str, Any]] = {}  # document-level metadata + is_deleted
-        self.lexical: Optional[LexicalIndex] = LexicalIndex(device) if bm25_index else None
+        self.lexical: Optional[LexicalIndex] = LexicalIndex(device, table=table) if bm25_index else None
         # metadata equality filters: per key, value text -> row ids, extended incrementally as rows are added
         self.filter_index: Dict[str, Dict[str, Any]] = {}
         # packed device bitmasks per (filter, include_deleted), valid for (rows, docs_epoch)
@@ -82,8 +84,17 @@ class _Collection:
         return self.native
 
 
-_REGISTRY: Dict[Tuple[str, int], _Collection] = {}
+_REGISTRY: Dict[Tuple[str, str, int], _Collection] = {}
+_TABLES: Dict[Tuple[str, int], TableStats] = {}      # BM25 statistics span the collections of one database
 _REGISTRY_LOCK = threading.Lock()
+
+
+def _database_key(pg_config: Optional[Dict[str, Any]]) -> str:
+    """Which ``document_chunks`` table a store object talks to: the reference opens ``psycopg2.connect(**pg_config)``
+    (postgres_vectorstore.py:94-98), so two configs naming the same server and database share the table."""
+    if not pg_config:
+        return "default"
+    return "{}:{}/{}".format(pg_config.get("host", ""), pg_config.get("port", ""), pg_config.get("dbname", ""))
 
 
 class B200VectorStore(_VectorStoreBase):
@@ -112,11 +123,13 @@ class B200VectorStore(_VectorStoreBase):
         if distance_metric not in self._distance_ops:
             raise ValueError(f"distance_metric must be one of {list(self._distance_ops.keys())}")
         self._distance_op = self._distance_ops[distance_metric]
-        key = (collection_name, int(device))
+        db = _database_key(pg_config)
+        key = (db, collection_name, int(device))
         with _REGISTRY_LOCK:
             coll = _REGISTRY.get(key)
             if coll is None:
-                coll = _Collection(collection_name, distance_metric, int(device), storage_dtype, bm25_index)
+                table = _TABLES.setdefault((db, int(device)), TableStats())
+                coll = _Collection(collection_name, distance_metric, int(device), storage_dtype, bm25_index, table)
                 _REGISTRY[key] = coll
             elif coll.metric != distance_metric:
                 raise ValueError(
@@ -126,11 +139,14 @@ class B200VectorStore(_VectorStoreBase):
 
     # ---- registry helpers (no reference counterpart: the table outlives the Python object) ------
     @classmethod
-    def drop_collection(cls, collection_name: str, device: int = 0) -> None:
+    def drop_collection(cls, collection_name: str, device: int = 0, pg_config: Optional[Dict[str, Any]] = None) -> None:
         with _REGISTRY_LOCK:
-            coll = _REGISTRY.pop((collection_name, int(device)), None)
-        if coll is not None and coll.native is not None:
-            coll.native.close()
+            coll = _REGISTRY.pop((_database_key(pg_config), collection_name, int(device)), None)
+        if coll is not None:
+            if coll.lexical is not None:
+                coll.lexical.detach()
+            if coll.native is not None:
+                coll.native.close()
 
     @property
     def embeddings(self):
@@ -419,7 +435,11 @@ def _upload_mask_words(words: np.ndarray, device: int):
 
 
 def _json_text(v: Any) -> str:
-    """What ``metadata->>'key'`` yields for a JSON value (booleans are lower-case in JSON text)."""
-    if isinstance(v, bool):
-        return "true" if v else "false"
-    return str(v)
+    """What ``metadata->>'key'`` yields for a JSON value: strings as they are, everything else as JSON text
+    (booleans lower-case, nested objects / arrays in jsonb's ``{"k": v}`` spelling)."""
+    if isinstance(v, str):
+        return v
+    try:
+        return json.dumps(v)
+    except (TypeError, ValueError):
+        return str(v)

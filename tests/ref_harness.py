@@ -408,22 +408,17 @@ class B200Impl:
         self.Document = vs.Document
         self.HybridRetriever, self.SemanticRetriever, self.GradingRetriever = r.HybridRetriever, r.SemanticRetriever, r.GradingRetriever
         self._bm25: Dict[str, bool] = {}
-        self._collections: List[str] = []
+        self._collections: List[Any] = []
 
     def database(self, name: str, bm25_index: bool = True):
         self._bm25[name] = bm25_index
 
-    def _coll(self, db, collection):
-        name = f"conf::{db}::{collection}"
-        if name not in self._collections:
-            self._collections.append(name)
-        return name
-
     def store(self, db: str, collection: str, metric: str, emb):
-        s = self.vs.B200VectorStore(None, emb, collection_name=self._coll(db, collection), distance_metric=metric,
-                                    bm25_index=self._bm25[db])
-        s._collection_name = collection      # the name stamped into metadata["collection"] is the reference's
-        return s
+        cfg = {"host": "conformance", "dbname": db}
+        if (collection, cfg) not in self._collections:
+            self._collections.append((collection, cfg))
+        return self.vs.B200VectorStore(cfg, emb, collection_name=collection, distance_metric=metric,
+                                       bm25_index=self._bm25[db])
 
     def from_texts(self, db, collection, metric, emb, texts, metadatas, **kw):
         s = self.store(db, collection, metric, emb)
@@ -434,8 +429,8 @@ class B200Impl:
         store.register_document(document_id, **fields)
 
     def close(self):
-        for name in self._collections:
-            self.vs.B200VectorStore.drop_collection(name)
+        for name, cfg in self._collections:
+            self.vs.B200VectorStore.drop_collection(name, pg_config=cfg)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -527,8 +522,7 @@ def run_scenario(impl) -> Dict[str, Any]:
     T["filter_bool_json_str"] = R(st.similarity_search_with_score(q1, k=6, filter={"flag": "true"}))
     T["filter_missing_key"] = R(st.similarity_search_with_score(q1, k=6, filter={"nope": "x"}))
     T["filter_nested"] = R(st.similarity_search_with_score(q1, k=3, filter={"nested": '{"x": 4}'}))
-    T["filter_none"] = R(st.similarity_search_with_score(q1, k=3, filter=None) if impl.name != "reference" else
-                         st.similarity_search_with_score(q1, k=3, filter={}))
+    T["filter_empty_dict"] = R(st.similarity_search_with_score(q1, k=3, filter={}))
     # ---- soft-deleted documents (:304-308) ------------------------------------------------------------------
     impl.register_document("main", st, 2, resource_hash="hash-2", display_name="Doc Two", source_type="web", url=None, is_deleted=True)
     T["doc2_deleted"] = R(st.similarity_search_with_score(q2, k=8))

@@ -13,8 +13,10 @@ from oracle import oracle as orc
 
 def bm25_from_csr(ix, query):
     """What archi_bm25_accumulate computes (include/archi_b200.h), on the host CSR."""
+    for m in ix.table.members:       # the statistics are table-wide: every index of the table must be current
+        m._term_keys, m._df, m._post_ptr, _, _, _, m._n_live, m._avgdl = m._host_csr()
     term_keys, df, post_ptr, doc_ids, tfs, dl, n_live, avgdl = ix._host_csr()
-    ix._term_keys, ix._df, ix._post_ptr, ix._n_live, ix._avgdl = term_keys, df, post_ptr, n_live, avgdl
+    avgdl = ix.avgdl()
     out = np.zeros(len(ix), dtype=np.float64)
     touched = np.zeros(len(ix), dtype=bool)
     for t in ix.query_terms(query):
