@@ -26,7 +26,7 @@ EXPORTS = [
     "archi_store_info", "archi_store_reserve", "archi_store_reset", "archi_store_append",
     "archi_store_delete_rows", "archi_store_read_rows", "archi_store_save", "archi_store_load",
     "archi_pool_normalize", "archi_pool_normalize_append", "archi_search", "archi_hybrid_search",
-    "archi_bm25_accumulate", "archi_merge_topk", "archi_merge_topk_strided", "archi_store_last_stats", "archi_store_set_timing",
+    "archi_hybrid_search_terms", "archi_bm25_accumulate", "archi_merge_topk", "archi_merge_topk_strided", "archi_store_last_stats", "archi_store_set_timing",
     "archi_exchange_create", "archi_exchange_local_handle", "archi_exchange_connect", "archi_exchange_merge_topk",
     "archi_exchange_status", "archi_exchange_destroy",
 ]
@@ -35,7 +35,15 @@ EXPORTS = [
 class SearchStats(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int), ("passes", ctypes.c_int), ("grid", ctypes.c_int),
                 ("unverified_queries", ctypes.c_int), ("last_kernel_ms", ctypes.c_double),
-                ("coarse_dtype", ctypes.c_int), ("coarse_launches", ctypes.c_int)]
+                ("coarse_dtype", ctypes.c_int), ("coarse_launches", ctypes.c_int), ("unproven_queries", ctypes.c_int)]
+
+
+class Bm25Terms(ctypes.Structure):
+    """archi_bm25_terms_t (include/archi_b200.h)."""
+    _fields_ = [("n_terms", ctypes.c_int), ("term_query", ctypes.c_void_p), ("post_start", ctypes.c_void_p),
+                ("post_end", ctypes.c_void_p), ("idf", ctypes.c_void_p), ("doc_ids_dev", ctypes.c_void_p),
+                ("tfs_dev", ctypes.c_void_p), ("doc_len_dev", ctypes.c_void_p), ("avgdl", ctypes.c_float),
+                ("k1", ctypes.c_float), ("b", ctypes.c_float), ("sign", ctypes.c_float)]
 
 
 class NativeError(RuntimeError):
@@ -82,6 +90,8 @@ def lib() -> ctypes.CDLL:
     L.archi_search.argtypes = [c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_i64, c_p]
     L.archi_hybrid_search.argtypes = [c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_i, c_p, c_p, c_i,
                                       c_i64, c_p]
+    L.archi_hybrid_search_terms.argtypes = [c_p, c_p, c_i, c_i, c_i, c_f, c_f, ctypes.POINTER(Bm25Terms), c_p, c_i, c_p, c_p,
+                                            c_i, c_i64, c_p, pint]
     L.archi_bm25_accumulate.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p]
     L.archi_merge_topk.argtypes = [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
     L.archi_merge_topk_strided.argtypes = [c_i, c_p, c_p, c_i64, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p]

@@ -285,6 +285,31 @@ class LexicalIndex:
     def avgdl(self) -> float:
         return self.table.avgdl() if len(self.table.members) > 1 else self._avgdl
 
+    def posting_ranges(self, query):
+        """(starts int64 [t], ends int64 [t], idf float32 [t]) of the query's term occurrences that have postings
+        in this index -- what archi_hybrid_search_terms / archi_bm25_accumulate take.  idf uses the table-wide
+        statistics."""
+        self.table.refresh()
+        if self._dirty:
+            self._rebuild()
+        terms = np.asarray([t for t in self.query_terms(query) if 0 <= t < self._df.size and self._df[t] > 0], dtype=np.int64)
+        if terms.size == 0:
+            z = np.empty(0, dtype=np.int64)
+            return z, z.copy(), np.empty(0, dtype=np.float32)
+        if len(self.table.members) == 1:
+            df, n = self._df[terms].astype(np.float64), float(self._n_live)
+        else:
+            df, n = self.table.df_of_keys(self._term_keys[terms]).astype(np.float64), float(self.table.n_live())
+        idf = np.log(1.0 + (n - df + 0.5) / (df + 0.5)).astype(np.float32)
+        return self._post_ptr[terms].astype(np.int64), self._post_ptr[terms + 1].astype(np.int64), idf
+
+    def device_arrays(self):
+        """(doc_ids int32, tfs int32, doc_len float32) CUDA tensors of the posting lists (built on demand)."""
+        self.table.refresh()
+        if self._dirty:
+            self._rebuild()
+        return self._doc_ids_dev, self._tfs_dev, self._doc_len_dev
+
     def score(self, query, out=None):
         """Dense fp32 [rows] BM25 scores of ``query`` on the GPU, 0 where no term matches."""
         import torch

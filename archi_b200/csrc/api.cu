@@ -69,6 +69,8 @@ static void free_workspace(Workspace &w)
     if (w.out_ids) cudaFree(w.out_ids);
     if (w.ev0) cudaEventDestroy(w.ev0);
     if (w.ev1) cudaEventDestroy(w.ev1);
+    if (w.resc_key) cudaFree(w.resc_key);
+    if (w.resc_id) cudaFree(w.resc_id);
     w = Workspace();
 }
 
@@ -104,43 +106,57 @@ static int ensure_out_staging(archi_store *s, int64_t elems)
     return ARCHI_OK;
 }
 
-// The common body of archi_search / archi_hybrid_search.
-static int search_impl(archi_store *s, const float *queries, int queries_loc, int nq, int k,
-                       const uint32_t *filter_mask_dev, int include_deleted, int path, int hybrid,
-                       float w_sem, float w_bias, const float *bias_dev, float *out_scores,
-                       int64_t *out_ids, int out_loc, int64_t id_offset, void *stream)
+// Host-driven exact re-scan of every query of a tensor launch whose proof failed (flags in tws.unverified):
+// only needed when more proofs failed than the device-side rescue list holds, and only possible with host
+// outputs (the call synchronises anyway).  Synchronises `st`.
+static int rescan_flagged(archi_store *s, ScanArgs a, const float *q_dev, int nb, int k, float *o_scores, int64_t *o_ids,
+                          int64_t id_offset, cudaStream_t st)
 {
-    ARCHI_REQUIRE(s != nullptr, "search: null store");
-    ARCHI_REQUIRE(nq >= 0 && k >= 0, "search: nq=%d k=%d must be non-negative", nq, k);
-    ARCHI_REQUIRE(nq == 0 || queries != nullptr, "search: null queries");
-    ARCHI_REQUIRE(nq == 0 || k == 0 || (out_scores && out_ids), "search: null outputs");
-    ARCHI_REQUIRE(queries_loc == ARCHI_HOST || queries_loc == ARCHI_DEVICE, "search: bad queries_loc");
-    ARCHI_REQUIRE(out_loc == ARCHI_HOST || out_loc == ARCHI_DEVICE, "search: bad out_loc");
-    ARCHI_REQUIRE(path == ARCHI_PATH_AUTO || path == ARCHI_PATH_STREAM || path == ARCHI_PATH_TENSOR,
-                  "search: bad path %d", path);
-    if (nq == 0 || k == 0) return ARCHI_OK;
-
-    std::lock_guard<std::mutex> lock(s->mu);
-    ARCHI_DEVICE_GUARD(s->device);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-
-    const float *q_dev = queries;
-    {
-        const int rc = ensure_query_staging(s, nq);
+    std::vector<int> flags(nb);
+    ARCHI_CUDA(cudaMemcpyAsync(flags.data(), s->tws.unverified, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARCHI_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < nb; ++i) {
+        if (!flags[i]) continue;
+        a.nqb = 1;
+        a.k = k;
+        a.queries = q_dev + (size_t)i * s->dim;
+        a.bias = nullptr;
+        a.cursor_key = nullptr;
+        a.cursor_id = nullptr;
+        int g2 = 0;
+        int rc = launch_scan(s, a, st, &g2);
+        if (rc != ARCHI_OK) return rc;
+        rc = launch_scan_finalize(s, a, g2, k, 0, o_scores + (size_t)i * k, o_ids + (size_t)i * k, id_offset, nullptr,
+                                  nullptr, st);
         if (rc != ARCHI_OK) return rc;
     }
-    if (queries_loc == ARCHI_HOST) {
-        ARCHI_CUDA(cudaMemcpyAsync(s->ws.q_dev, queries, (size_t)nq * s->dim * sizeof(float),
-                                   cudaMemcpyHostToDevice, st));
-        q_dev = s->ws.q_dev;
-    }
-    float *o_scores = out_scores;
-    int64_t *o_ids = out_ids;
-    if (out_loc == ARCHI_HOST) {
-        if (ensure_out_staging(s, (int64_t)nq * k) != ARCHI_OK) return ARCHI_ECUDA;
-        o_scores = s->ws.out_scores;
-        o_ids = s->ws.out_ids;
-    }
+    return ARCHI_OK;
+}
+
+// The store's buffers and scratch are shared by every call on the handle: a call on another stream than the
+// previous one first waits (on the device) for that call's work.
+static int order_after_previous(archi_store *s, cudaStream_t st)
+{
+    if (!s->order_ev) ARCHI_CUDA(cudaEventCreateWithFlags(&s->order_ev, cudaEventDisableTiming));
+    else if (s->order_stream != st) ARCHI_CUDA(cudaStreamWaitEvent(st, s->order_ev, 0));
+    return ARCHI_OK;
+}
+
+static int mark_done(archi_store *s, cudaStream_t st)
+{
+    if (!s->order_ev) ARCHI_CUDA(cudaEventCreateWithFlags(&s->order_ev, cudaEventDisableTiming));
+    ARCHI_CUDA(cudaEventRecord(s->order_ev, st));
+    s->order_stream = st;
+    return ARCHI_OK;
+}
+
+// The search proper: queries and outputs on the device, the handle's mutex held by the caller.  Nothing here
+// waits for the GPU unless `host_sync_ok` (the caller synchronises anyway) and a batch > 2048 needs it.
+static int search_core(archi_store *s, const float *q_dev, int nq, int k, const uint32_t *filter_mask_dev,
+                       int include_deleted, int path, int hybrid, float w_sem, float w_bias, const float *bias_dev,
+                       float *o_scores, int64_t *o_ids, int64_t id_offset, cudaStream_t st, bool host_sync_ok,
+                       bool *used_tensor)
+{
     if (s->timing && !s->ws.ev0) {
         ARCHI_CUDA(cudaEventCreate(&s->ws.ev0));
         ARCHI_CUDA(cudaEventCreate(&s->ws.ev1));
@@ -157,6 +173,7 @@ static int search_impl(archi_store *s, const float *queries, int queries_loc, in
     } else if (path == ARCHI_PATH_AUTO) {
         use_tensor = !hybrid && nq >= kTensorMinBatch && tensor_path_supported(s, k);
     }
+    if (used_tensor) *used_tensor = use_tensor;
 
     ScanArgs a;
     a.corpus = s->data;
@@ -173,80 +190,317 @@ static int search_impl(archi_store *s, const float *queries, int queries_loc, in
     a.w_bias = w_bias;
     a.bias_stride = s->rows;
 
-    int passes = 0, grid = 0, unverified_total = 0;
+    int passes = 0, grid = 0;
     double kernel_ms = 0.0;
+    TensorWorkspace &tw = s->tws;
+    tw.verdict_pending = false;
+    tw.verdict_launches = 0;
     if (use_tensor) {
-        std::vector<int> flags;
+        // Everything is enqueued without a host round trip: coarse launches, select + exact rescoring +
+        // proof, and the device-driven exact re-scan of the queries whose proof failed (a no-op costing a few
+        // microseconds when there are none).  The per-launch counters travel to pinned memory behind an event
+        // and are read when the host next synchronises anyway (host outputs, archi_store_last_stats).
+        const bool multi = nq > kTensorMaxBatch;
         for (int q0 = 0; q0 < nq; q0 += kTensorMaxBatch) {
             const int nb = nq - q0 < kTensorMaxBatch ? nq - q0 : kTensorMaxBatch;
-            int n_unv = 0;
+            const int slot = tw.verdict_launches < 64 ? tw.verdict_launches : 63;
             double ms = 0.0;
-            flags.assign(nb, 0);
+            int max_sel = 0;
             int rc = launch_tensor_search(s, q_dev + (size_t)q0 * s->dim, nb, k, filter_mask_dev, include_deleted,
-                                          o_scores + (size_t)q0 * k, o_ids + (size_t)q0 * k, id_offset, st, &n_unv,
-                                          flags.data(), &ms);
+                                          o_scores + (size_t)q0 * k, o_ids + (size_t)q0 * k, id_offset, st, &max_sel, &ms);
             if (rc != ARCHI_OK) return rc;
             kernel_ms += ms;
             ++passes;
             grid = s->stats.grid;
-            // queries whose exactness proof failed are answered by the exact streaming scan
-            for (int i = 0; n_unv > 0 && i < nb; ++i) {
-                if (!flags[i]) continue;
-                ++unverified_total;
-                a.nqb = 1;
-                a.k = k;
-                a.queries = q_dev + (size_t)(q0 + i) * s->dim;
-                a.bias = nullptr;
-                a.cursor_key = nullptr;
-                a.cursor_id = nullptr;
-                int g2 = 0;
-                rc = launch_scan(s, a, st, &g2);
-                if (rc != ARCHI_OK) return rc;
-                rc = launch_scan_finalize(s, a, g2, k, 0, o_scores + (size_t)(q0 + i) * k, o_ids + (size_t)(q0 + i) * k,
-                                          id_offset, nullptr, nullptr, st);
-                if (rc != ARCHI_OK) return rc;
+            a.k = k;
+            a.queries = q_dev + (size_t)q0 * s->dim;
+            a.bias = nullptr;
+            a.cursor_key = nullptr;
+            a.cursor_id = nullptr;
+            rc = launch_rescue(s, a, tw.unv_list, tw.unv_count, max_sel, o_scores + (size_t)q0 * k,
+                               o_ids + (size_t)q0 * k, id_offset, st);
+            if (rc != ARCHI_OK) return rc;
+            ARCHI_CUDA(cudaMemcpyAsync(tw.h_verdict + slot, tw.unv_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+            tw.verdict_max_sel[slot] = max_sel;
+            tw.verdict_launches = slot + 1;
+            if (multi && host_sync_ok && nb > max_sel) {
+                // more than one launch shares the flag buffer: settle this one before the next overwrites it
+                ARCHI_CUDA(cudaStreamSynchronize(st));
+                if (tw.h_verdict[slot] > max_sel) {
+                    rc = rescan_flagged(s, a, q_dev + (size_t)q0 * s->dim, nb, k, o_scores + (size_t)q0 * k,
+                                        o_ids + (size_t)q0 * k, id_offset, st);
+                    if (rc != ARCHI_OK) return rc;
+                }
             }
         }
+        ARCHI_CUDA(cudaEventRecord(tw.verdict_ev, st));
+        tw.verdict_pending = true;
     } else {
-    for (int q0 = 0; q0 < nq; q0 += kMaxQB) {
-        a.nqb = nq - q0 < kMaxQB ? nq - q0 : kMaxQB;
-        a.queries = q_dev + (size_t)q0 * s->dim;
-        a.bias = bias_dev ? bias_dev + (size_t)q0 * s->rows : nullptr;
-        for (int col0 = 0; col0 < k; col0 += kMaxListK) {
-            a.k = k - col0 < kMaxListK ? k - col0 : kMaxListK;
-            a.cursor_key = col0 > 0 ? s->ws.cursor_key : nullptr;
-            a.cursor_id = col0 > 0 ? s->ws.cursor_id : nullptr;
-            if (s->timing) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
-            int rc = launch_scan(s, a, st, &grid);
-            if (rc != ARCHI_OK) return rc;
-            if (s->timing) {
-                ARCHI_CUDA(cudaEventRecord(s->ws.ev1, st));
-                ARCHI_CUDA(cudaEventSynchronize(s->ws.ev1));
-                float ms = 0.f;
-                ARCHI_CUDA(cudaEventElapsedTime(&ms, s->ws.ev0, s->ws.ev1));
-                kernel_ms += ms;
+        for (int q0 = 0; q0 < nq; q0 += kMaxQB) {
+            a.nqb = nq - q0 < kMaxQB ? nq - q0 : kMaxQB;
+            a.queries = q_dev + (size_t)q0 * s->dim;
+            a.bias = bias_dev ? bias_dev + (size_t)q0 * s->rows : nullptr;
+            for (int col0 = 0; col0 < k; col0 += kMaxListK) {
+                a.k = k - col0 < kMaxListK ? k - col0 : kMaxListK;
+                a.cursor_key = col0 > 0 ? s->ws.cursor_key : nullptr;
+                a.cursor_id = col0 > 0 ? s->ws.cursor_id : nullptr;
+                if (s->timing) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
+                int rc = launch_scan(s, a, st, &grid);
+                if (rc != ARCHI_OK) return rc;
+                if (s->timing) {
+                    ARCHI_CUDA(cudaEventRecord(s->ws.ev1, st));
+                    ARCHI_CUDA(cudaEventSynchronize(s->ws.ev1));
+                    float ms = 0.f;
+                    ARCHI_CUDA(cudaEventElapsedTime(&ms, s->ws.ev0, s->ws.ev1));
+                    kernel_ms += ms;
+                }
+                const bool more = col0 + a.k < k;
+                rc = launch_scan_finalize(s, a, grid, k, col0, o_scores + (size_t)q0 * k, o_ids + (size_t)q0 * k,
+                                          id_offset, more ? s->ws.cursor_key : nullptr,
+                                          more ? s->ws.cursor_id : nullptr, st);
+                if (rc != ARCHI_OK) return rc;
+                ++passes;
             }
-            const bool more = col0 + a.k < k;
-            rc = launch_scan_finalize(s, a, grid, k, col0, o_scores + (size_t)q0 * k, o_ids + (size_t)q0 * k,
-                                      id_offset, more ? s->ws.cursor_key : nullptr,
-                                      more ? s->ws.cursor_id : nullptr, st);
-            if (rc != ARCHI_OK) return rc;
-            ++passes;
         }
-    }
     }
     s->stats.path = use_tensor ? ARCHI_PATH_TENSOR : ARCHI_PATH_STREAM;
     s->stats.passes = passes;
     s->stats.grid = grid;
-    s->stats.unverified_queries = unverified_total;
+    s->stats.unverified_queries = 0;      // tensor path: filled in lazily from the pinned verdict (archi_store_last_stats)
     s->stats.last_kernel_ms = passes ? kernel_ms / passes : 0.0;
+    return ARCHI_OK;
+}
 
+// Query / output staging shared by the search entry points.  With host outputs the device-side staging
+// buffers are returned and `finish_outputs` copies them back and synchronises.
+struct Staged {
+    const float *q_dev;
+    float *o_scores;
+    int64_t *o_ids;
+};
+
+static int stage_io(archi_store *s, const float *queries, int queries_loc, int nq, int k, float *out_scores,
+                    int64_t *out_ids, int out_loc, cudaStream_t st, Staged *io)
+{
+    io->q_dev = queries;
+    int rc = ensure_query_staging(s, nq);
+    if (rc != ARCHI_OK) return rc;
+    if (queries_loc == ARCHI_HOST) {
+        ARCHI_CUDA(cudaMemcpyAsync(s->ws.q_dev, queries, (size_t)nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+        io->q_dev = s->ws.q_dev;
+    }
+    io->o_scores = out_scores;
+    io->o_ids = out_ids;
     if (out_loc == ARCHI_HOST) {
-        ARCHI_CUDA(cudaMemcpyAsync(out_scores, o_scores, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-        ARCHI_CUDA(cudaMemcpyAsync(out_ids, o_ids, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        ARCHI_CUDA(cudaStreamSynchronize(st));
+        if (ensure_out_staging(s, (int64_t)nq * k) != ARCHI_OK) return ARCHI_ECUDA;
+        io->o_scores = s->ws.out_scores;
+        io->o_ids = s->ws.out_ids;
     }
     return ARCHI_OK;
+}
+
+static int copy_outputs_to_host(const Staged &io, int nq, int k, float *out_scores, int64_t *out_ids, cudaStream_t st)
+{
+    ARCHI_CUDA(cudaMemcpyAsync(out_scores, io.o_scores, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ARCHI_CUDA(cudaMemcpyAsync(out_ids, io.o_ids, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    ARCHI_CUDA(cudaStreamSynchronize(st));
+    return ARCHI_OK;
+}
+
+static int check_search_args(archi_store *s, const float *queries, int queries_loc, int nq, int k, float *out_scores,
+                             int64_t *out_ids, int out_loc)
+{
+    ARCHI_REQUIRE(s != nullptr, "search: null store");
+    ARCHI_REQUIRE(nq >= 0 && k >= 0, "search: nq=%d k=%d must be non-negative", nq, k);
+    ARCHI_REQUIRE(nq == 0 || queries != nullptr, "search: null queries");
+    ARCHI_REQUIRE(nq == 0 || k == 0 || (out_scores && out_ids), "search: null outputs");
+    ARCHI_REQUIRE(queries_loc == ARCHI_HOST || queries_loc == ARCHI_DEVICE, "search: bad queries_loc");
+    ARCHI_REQUIRE(out_loc == ARCHI_HOST || out_loc == ARCHI_DEVICE, "search: bad out_loc");
+    return ARCHI_OK;
+}
+
+// The common body of archi_search / archi_hybrid_search.
+static int search_impl(archi_store *s, const float *queries, int queries_loc, int nq, int k,
+                       const uint32_t *filter_mask_dev, int include_deleted, int path, int hybrid,
+                       float w_sem, float w_bias, const float *bias_dev, float *out_scores,
+                       int64_t *out_ids, int out_loc, int64_t id_offset, void *stream)
+{
+    int rc = check_search_args(s, queries, queries_loc, nq, k, out_scores, out_ids, out_loc);
+    if (rc != ARCHI_OK) return rc;
+    ARCHI_REQUIRE(path == ARCHI_PATH_AUTO || path == ARCHI_PATH_STREAM || path == ARCHI_PATH_TENSOR,
+                  "search: bad path %d", path);
+    if (nq == 0 || k == 0) return ARCHI_OK;
+
+    std::lock_guard<std::mutex> lock(s->mu);
+    ARCHI_DEVICE_GUARD(s->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if ((rc = order_after_previous(s, st)) != ARCHI_OK) return rc;
+    Staged io;
+    if ((rc = stage_io(s, queries, queries_loc, nq, k, out_scores, out_ids, out_loc, st, &io)) != ARCHI_OK) return rc;
+    bool used_tensor = false;
+    rc = search_core(s, io.q_dev, nq, k, filter_mask_dev, include_deleted, path, hybrid, w_sem, w_bias, bias_dev,
+                     io.o_scores, io.o_ids, id_offset, st, out_loc == ARCHI_HOST, &used_tensor);
+    if (rc != ARCHI_OK) return rc;
+    if (out_loc == ARCHI_HOST) {
+        if ((rc = copy_outputs_to_host(io, nq, k, out_scores, out_ids, st)) != ARCHI_OK) return rc;
+        TensorWorkspace &tw = s->tws;
+        if (used_tensor && nq <= kTensorMaxBatch && tw.h_verdict[0] > tw.verdict_max_sel[0]) {
+            // (only batches > 256 can get here) more proofs failed than the device-side rescue takes:
+            // re-scan every flagged query now and fetch the rows again
+            ScanArgs a;
+            a.corpus = s->data;
+            a.dtype = s->dtype;
+            a.n = s->rows;
+            a.dim = s->dim;
+            a.ld = s->ld;
+            a.metric = s->metric;
+            a.norm2 = s->norm2;
+            a.alive = include_deleted ? nullptr : s->alive;
+            a.filter = filter_mask_dev;
+            a.hybrid = 0;
+            a.w_sem = 1.f;
+            a.w_bias = 0.f;
+            a.bias_stride = s->rows;
+            if ((rc = rescan_flagged(s, a, io.q_dev, nq, k, io.o_scores, io.o_ids, id_offset, st)) != ARCHI_OK) return rc;
+            if ((rc = copy_outputs_to_host(io, nq, k, out_scores, out_ids, st)) != ARCHI_OK) return rc;
+        }
+    }
+    return mark_done(s, st);
+}
+
+// ---- hybrid over posting lists (hybrid.cu) --------------------------------------------------------------------
+// Dense-vector fallback for one query whose terms match a large part of the corpus: BM25 accumulated into a
+// [rows] vector (zeroed first), then the streaming scan with the fused bias term.
+static int hybrid_dense_vector_one(archi_store *s, const float *q_dev, int k, float w_sem, float w_bm25, const HybridTerms &t,
+                                   int pair0, int n_pairs, const uint32_t *filter, int include_deleted, float *o_scores,
+                                   int64_t *o_ids, int64_t id_offset, cudaStream_t st)
+{
+    HybridWorkspace &w = s->hws;
+    const size_t need = (size_t)(s->capacity > 0 ? s->capacity : 1) * sizeof(float);
+    if (!w.bias || w.bias_bytes < need) {
+        if (w.bias) cudaFree(w.bias);
+        w.bias = nullptr;
+        w.bias_bytes = 0;
+        ARCHI_CUDA(cudaMalloc(&w.bias, need));
+        w.bias_bytes = need;
+    }
+    ARCHI_CUDA(cudaMemsetAsync(w.bias, 0, (size_t)s->rows * sizeof(float), st));
+    for (int j = 0; j < n_pairs; ++j) {
+        const int64_t b0 = t.post_start[pair0 + j], b1 = t.post_end[pair0 + j];
+        int rc = launch_bm25(t.doc_ids_dev + b0, t.tfs_dev + b0, b1 - b0, t.idf[pair0 + j], t.doc_len_dev, t.avgdl, t.k1, t.b,
+                             t.sign, w.bias, st);
+        if (rc != ARCHI_OK) return rc;
+    }
+    return search_core(s, q_dev, 1, k, filter, include_deleted, ARCHI_PATH_STREAM, 1, w_sem, w_bm25, w.bias, o_scores, o_ids,
+                       id_offset, st, false, nullptr);
+}
+
+static int hybrid_terms_impl(archi_store *s, const float *queries, int queries_loc, int nq, int k, float w_sem, float w_bm25,
+                             const archi_bm25_terms_t *terms, const uint32_t *filter, int include_deleted, float *out_scores,
+                             int64_t *out_ids, int out_loc, int64_t id_offset, void *stream, int *out_path)
+{
+    int rc = check_search_args(s, queries, queries_loc, nq, k, out_scores, out_ids, out_loc);
+    if (rc != ARCHI_OK) return rc;
+    ARCHI_REQUIRE(terms != nullptr && terms->n_terms >= 0, "hybrid_search_terms: null terms");
+    ARCHI_REQUIRE(terms->n_terms == 0 || (terms->term_query && terms->post_start && terms->post_end && terms->idf &&
+                                          terms->doc_ids_dev && terms->tfs_dev && terms->doc_len_dev),
+                  "hybrid_search_terms: null posting arrays");
+    ARCHI_REQUIRE(terms->avgdl > 0.f, "hybrid_search_terms: avgdl must be positive");
+    if (out_path) *out_path = 0;
+    if (nq == 0 || k == 0) return ARCHI_OK;
+    HybridTerms t;
+    t.post_start = terms->post_start;
+    t.post_end = terms->post_end;
+    t.idf = terms->idf;
+    t.doc_ids_dev = terms->doc_ids_dev;
+    t.tfs_dev = terms->tfs_dev;
+    t.doc_len_dev = terms->doc_len_dev;
+    t.avgdl = terms->avgdl;
+    t.k1 = terms->k1;
+    t.b = terms->b;
+    t.sign = terms->sign;
+    // per-query term ranges (term_query ascending) and posting counts
+    std::vector<int> first(nq + 1, 0);
+    std::vector<long long> postings(nq, 0);
+    {
+        int prev = 0;
+        for (int j = 0; j < terms->n_terms; ++j) {
+            const int q = terms->term_query[j];
+            ARCHI_REQUIRE(q >= prev && q < nq, "hybrid_search_terms: term_query must be ascending and < nq");
+            ARCHI_REQUIRE(t.post_start[j] >= 0 && t.post_end[j] >= t.post_start[j], "hybrid_search_terms: bad posting range");
+            prev = q;
+            first[q + 1] = j + 1;
+            postings[q] += t.post_end[j] - t.post_start[j];
+        }
+        for (int q = 0; q < nq; ++q)
+            if (first[q + 1] < first[q]) first[q + 1] = first[q];
+    }
+
+    std::lock_guard<std::mutex> lock(s->mu);
+    ARCHI_DEVICE_GUARD(s->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if ((rc = order_after_previous(s, st)) != ARCHI_OK) return rc;
+    Staged io;
+    if ((rc = stage_io(s, queries, queries_loc, nq, k, out_scores, out_ids, out_loc, st, &io)) != ARCHI_OK) return rc;
+
+    // The sparse decomposition needs bm25 >= 0 (sign > 0), w_sem > 0 and w_bm25 >= 0; it pays while the terms of a
+    // query match a small part of the corpus.
+    const long long sparse_limit = s->rows / 8 > 4096 ? s->rows / 8 : 4096;
+    auto sparse_ok = [&](int q) {
+        return t.sign > 0.f && w_sem > 0.f && w_bm25 >= 0.f && k <= kMaxListK && s->rows > 0 && postings[q] <= sparse_limit &&
+               first[q + 1] - first[q] <= kHybMaxPairsHost;
+    };
+    int n_sparse = 0;
+    for (int q = 0; q < nq; ++q) n_sparse += sparse_ok(q) ? 1 : 0;
+    HybridWorkspace &w = s->hws;
+    if (n_sparse == nq) {
+        // dense top-k of the whole batch first (<= 256 queries per call: every failed proof is rescued on the device)
+        const size_t need_s = (size_t)nq * k * sizeof(float), need_i = (size_t)nq * k * sizeof(int64_t);
+        if (!w.dense_scores || w.dense_bytes < need_i) {
+            if (w.dense_scores) cudaFree(w.dense_scores);
+            if (w.dense_ids) cudaFree(w.dense_ids);
+            w.dense_scores = nullptr;
+            w.dense_ids = nullptr;
+            w.dense_bytes = 0;
+            ARCHI_CUDA(cudaMalloc(&w.dense_scores, need_s));
+            ARCHI_CUDA(cudaMalloc(&w.dense_ids, need_i));
+            w.dense_bytes = need_i;
+        }
+        for (int q0 = 0; q0 < nq; q0 += 256) {
+            const int nb = nq - q0 < 256 ? nq - q0 : 256;
+            rc = search_core(s, io.q_dev + (size_t)q0 * s->dim, nb, k, filter, include_deleted, ARCHI_PATH_AUTO, 0, 1.f, 0.f,
+                             nullptr, w.dense_scores + (size_t)q0 * k, w.dense_ids + (size_t)q0 * k, id_offset, st, false, nullptr);
+            if (rc != ARCHI_OK) return rc;
+        }
+        // rounds of <= kHybMaxSlotsHost queries and <= kHybMaxPairsHost terms
+        int q0 = 0;
+        while (q0 < nq) {
+            int q1 = q0, pairs = 0;
+            while (q1 < nq && q1 - q0 < kHybMaxSlotsHost && pairs + (first[q1 + 1] - first[q1]) <= kHybMaxPairsHost) {
+                pairs += first[q1 + 1] - first[q1];
+                ++q1;
+            }
+            std::vector<int> pair_slot(pairs > 0 ? pairs : 1);
+            for (int q = q0; q < q1; ++q)
+                for (int j = first[q]; j < first[q + 1]; ++j) pair_slot[j - first[q0]] = q - q0;
+            rc = launch_hybrid_sparse_round(s, io.q_dev + (size_t)q0 * s->dim, q1 - q0, k, w.dense_scores + (size_t)q0 * k,
+                                            w.dense_ids + (size_t)q0 * k, w_sem, w_bm25, t.sign, t, first[q0], pairs,
+                                            pair_slot.data(), filter, include_deleted, io.o_scores + (size_t)q0 * k,
+                                            io.o_ids + (size_t)q0 * k, id_offset, st);
+            if (rc != ARCHI_OK) return rc;
+            q0 = q1;
+        }
+        if (out_path) *out_path = 1;
+    } else {
+        for (int q = 0; q < nq; ++q) {
+            rc = hybrid_dense_vector_one(s, io.q_dev + (size_t)q * s->dim, k, w_sem, w_bm25, t, first[q], first[q + 1] - first[q],
+                                         filter, include_deleted, io.o_scores + (size_t)q * k, io.o_ids + (size_t)q * k, id_offset, st);
+            if (rc != ARCHI_OK) return rc;
+        }
+        if (out_path) *out_path = 2;
+    }
+    if (out_loc == ARCHI_HOST && (rc = copy_outputs_to_host(io, nq, k, out_scores, out_ids, st)) != ARCHI_OK) return rc;
+    return mark_done(s, st);
 }
 
 }  // namespace archi
@@ -308,6 +562,8 @@ int archi_store_destroy(archi_store_t *s)
     if (s->alive) cudaFree(s->alive);
     free_workspace(s->ws);
     free_tensor_workspace(s->tws);
+    free_hybrid_workspace(s->hws);
+    if (s->order_ev) cudaEventDestroy(s->order_ev);
     delete s;
     return ARCHI_OK;
 }
@@ -400,6 +656,10 @@ int archi_store_append(archi_store_t *s, const void *rows, int src_dtype, int sr
     if (n == 0) return ARCHI_OK;
     ARCHI_DEVICE_GUARD(s->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {
+        const int rc = order_after_previous(s, st);
+        if (rc != ARCHI_OK) return rc;
+    }
     if (s->rows + n > s->capacity) {
         int64_t want = s->capacity * 2 > s->rows + n ? s->capacity * 2 : s->rows + n;
         if (want < 1024) want = 1024;
@@ -427,7 +687,7 @@ int archi_store_append(archi_store_t *s, const void *rows, int src_dtype, int sr
     if (rc != ARCHI_OK) return rc;
     s->rows += n;
     s->epoch++;
-    return ARCHI_OK;
+    return mark_done(s, st);
 }
 
 int archi_store_delete_rows(archi_store_t *s, const int64_t *rows_host, int64_t n)
@@ -437,22 +697,31 @@ int archi_store_delete_rows(archi_store_t *s, const int64_t *rows_host, int64_t 
     if (n == 0) return ARCHI_OK;
     std::lock_guard<std::mutex> lock(s->mu);
     ARCHI_DEVICE_GUARD(s->device);
+    {
+        const int rc = order_after_previous(s, nullptr);     // runs on the legacy stream, after the previous call
+        if (rc != ARCHI_OK) return rc;
+    }
+    // one allocation: [n row ids | changed counter]; freed on every path
     long long *rows_dev = nullptr;
-    int *changed_dev = nullptr;
-    ARCHI_CUDA(cudaMalloc(&rows_dev, (size_t)n * sizeof(long long)));
-    ARCHI_CUDA(cudaMalloc(&changed_dev, sizeof(int)));
-    ARCHI_CUDA(cudaMemset(changed_dev, 0, sizeof(int)));
-    ARCHI_CUDA(cudaMemcpy(rows_dev, rows_host, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
-    int rc = launch_delete_rows(s, rows_dev, n, changed_dev, 0);
+    ARCHI_CUDA(cudaMalloc(&rows_dev, (size_t)(n + 1) * sizeof(long long)));
+    int *changed_dev = reinterpret_cast<int *>(rows_dev + n);
     int changed = 0;
-    if (rc == ARCHI_OK) {
-        ARCHI_CUDA(cudaMemcpy(&changed, changed_dev, sizeof(int), cudaMemcpyDeviceToHost));
-        s->deleted += changed;
-        s->epoch++;
+    int rc = ARCHI_OK;
+    cudaError_t e = cudaMemset(changed_dev, 0, sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemcpy(rows_dev, rows_host, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = launch_delete_rows(s, rows_dev, n, changed_dev, 0);
+        if (rc == ARCHI_OK) e = cudaMemcpy(&changed, changed_dev, sizeof(int), cudaMemcpyDeviceToHost);
     }
     cudaFree(rows_dev);
-    cudaFree(changed_dev);
-    return rc;
+    if (e != cudaSuccess) {
+        set_error("store_delete_rows: %s", cudaGetErrorString(e));
+        return ARCHI_ECUDA;
+    }
+    if (rc != ARCHI_OK) return rc;
+    s->deleted += changed;
+    s->epoch++;
+    return mark_done(s, nullptr);
 }
 
 int archi_store_read_rows(archi_store_t *s, int64_t first_row, int64_t n, float *out_host)
@@ -463,6 +732,10 @@ int archi_store_read_rows(archi_store_t *s, int64_t first_row, int64_t n, float 
                   (long long)first_row, (long long)(first_row + n), (long long)s->rows);
     if (n == 0) return ARCHI_OK;
     ARCHI_DEVICE_GUARD(s->device);
+    {
+        const int rc = order_after_previous(s, nullptr);
+        if (rc != ARCHI_OK) return rc;
+    }
     float *tmp = nullptr;
     ARCHI_CUDA(cudaMalloc(&tmp, (size_t)n * s->dim * sizeof(float)));
     int rc = launch_read_rows(s, first_row, n, tmp, 0);
@@ -598,6 +871,10 @@ int archi_pool_normalize_append(archi_store_t *s, const void *hidden_dev, int hi
     if (out_first_row) *out_first_row = s->rows;
     if (B == 0) return ARCHI_OK;
     ARCHI_DEVICE_GUARD(s->device);
+    {
+        const int rc = order_after_previous(s, reinterpret_cast<cudaStream_t>(stream));
+        if (rc != ARCHI_OK) return rc;
+    }
     if (s->rows + B > s->capacity) {
         int64_t want = s->capacity * 2 > s->rows + B ? s->capacity * 2 : s->rows + B;
         if (want < 1024) want = 1024;
@@ -611,7 +888,7 @@ int archi_pool_normalize_append(archi_store_t *s, const void *hidden_dev, int hi
     if (rc != ARCHI_OK) return rc;
     s->rows += B;
     s->epoch++;
-    return ARCHI_OK;
+    return mark_done(s, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- search -------------------------------------------------------------------------------------------
@@ -629,6 +906,15 @@ int archi_hybrid_search(archi_store_t *s, const float *queries, int queries_loc,
 {
     return search_impl(s, queries, queries_loc, nq, k, filter_mask_dev, include_deleted, ARCHI_PATH_STREAM, 1, w_sem,
                        w_bm25, bm25_dev, out_scores, out_ids, out_loc, id_offset, stream);
+}
+
+int archi_hybrid_search_terms(archi_store_t *s, const float *queries, int queries_loc, int nq, int k, float w_sem,
+                              float w_bm25, const archi_bm25_terms_t *terms, const uint32_t *filter_mask_dev,
+                              int include_deleted, float *out_scores, int64_t *out_ids, int out_loc, int64_t id_offset,
+                              void *stream, int *out_path)
+{
+    return hybrid_terms_impl(s, queries, queries_loc, nq, k, w_sem, w_bm25, terms, filter_mask_dev, include_deleted,
+                             out_scores, out_ids, out_loc, id_offset, stream, out_path);
 }
 
 int archi_bm25_accumulate(const int64_t *post_start_host, const int64_t *post_end_host, int n_terms,
@@ -681,6 +967,18 @@ int archi_store_last_stats(archi_store_t *s, archi_search_stats_t *out)
 {
     ARCHI_REQUIRE(s && out, "store_last_stats: null argument");
     std::lock_guard<std::mutex> lock(s->mu);
+    TensorWorkspace &tw = s->tws;
+    if (tw.verdict_pending) {
+        ARCHI_DEVICE_GUARD(s->device);
+        ARCHI_CUDA(cudaEventSynchronize(tw.verdict_ev));
+        int total = 0;
+        for (int i = 0; i < tw.verdict_launches; ++i) total += tw.h_verdict[i];
+        s->stats.unverified_queries = total;
+        int sticky = 0;
+        ARCHI_CUDA(cudaMemcpy(&sticky, tw.sticky_dev, sizeof(int), cudaMemcpyDeviceToHost));
+        s->stats.unproven_queries = sticky;
+        tw.verdict_pending = false;
+    }
     *out = s->stats;
     return ARCHI_OK;
 }

@@ -65,6 +65,10 @@ struct Workspace {
     int64_t *out_ids = nullptr;
     int64_t out_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // partial lists of the device-driven rescue scan: [passes][grid][kMaxQB][kMaxListK]
+    float *resc_key = nullptr;
+    int *resc_id = nullptr;
+    long long resc_elems = 0;
 };
 
 // scratch of the tensor-core path (tensor.cu)
@@ -87,7 +91,47 @@ struct TensorWorkspace {
     int64_t maxnorm_epoch = -1;
     int64_t aux_epoch = -1;
     bool aux_alive = false, aux_had_filter = false;
+    // queries whose exactness proof failed: device list [unv_cap] filled by tc_select_kernel, re-scanned by
+    // the device-driven rescue launches; the count travels to pinned host memory behind `verdict_ev`
+    int *unv_list = nullptr;     size_t unv_list_bytes = 0;
+    int *unv_count = nullptr;    // device counter of the current launch (lives behind the flags of `unverified`)
+    int *h_verdict = nullptr;    // pinned [64]: unproven queries of each tensor launch of the last search
+    int verdict_max_sel[64];     // ... and how many of them the device-side rescue could take
+    int verdict_launches = 0;
+    cudaEvent_t verdict_ev = nullptr;
+    bool verdict_pending = false;
+    int *sticky_dev = nullptr;   // device [1]: queries ever returned as id -1 / NaN because the rescue list was full
+    // TMA descriptors are rebuilt only when what they describe changes
+    unsigned char tmap_q[128] __attribute__((aligned(64)));
+    unsigned char tmap_c[128] __attribute__((aligned(64)));
+    const void *tmq_base = nullptr;  long long tmq_rows = -1;  int tmq_ld = 0, tmq_f32 = -1;
+    const void *tmc_base = nullptr;  long long tmc_rows = -1;  int tmc_ld = 0, tmc_f32 = -1, tmc_box = 0;
 };
+
+// scratch of the posting-list hybrid search (hybrid.cu)
+struct HybridWorkspace {
+    unsigned long long *acc = nullptr;  size_t acc_bytes = 0;   // [slots][capacity] BM25 sums, 32.32 fixed point, all zero between calls
+    bool acc_dirty = false;
+    int *cand_doc = nullptr;            size_t cand_doc_bytes = 0;
+    float *cand_bm = nullptr;           size_t cand_bm_bytes = 0;
+    int *cand_cnt = nullptr;            size_t cand_cnt_bytes = 0;
+    float *part_key = nullptr;          size_t part_key_bytes = 0;
+    int *part_id = nullptr;             size_t part_id_bytes = 0;
+    float *bias = nullptr;              size_t bias_bytes = 0;    // dense-vector fallback: [capacity] BM25 per row
+    float *dense_scores = nullptr;      // dense top-k of the batch
+    int64_t *dense_ids = nullptr;       size_t dense_bytes = 0;
+};
+
+// the query terms of a hybrid search: host arrays indexed by (query, term) occurrence + the device posting lists
+struct HybridTerms {
+    const int64_t *post_start, *post_end;
+    const float *idf;
+    const int32_t *doc_ids_dev, *tfs_dev;
+    const float *doc_len_dev;
+    float avgdl, k1, b, sign;
+};
+constexpr int kHybMaxPairsHost = 96;   // = kHybMaxPairs / kHybMaxSlots of hybrid.cu
+constexpr int kHybMaxSlotsHost = 16;
 
 }  // namespace archi
 
@@ -108,8 +152,13 @@ struct archi_store {
     archi_search_stats_t stats{};
     archi::Workspace ws;
     archi::TensorWorkspace tws;
+    archi::HybridWorkspace hws;
     int64_t epoch = 0;        // bumped whenever rows / tombstones change (invalidates cached aux)
     int64_t reset_epoch = 0;  // bumped when existing rows are discarded or moved (reset / load)
+    // stream ordering between calls on one handle (the buffers and scratch are shared): recorded at the end of
+    // every call that enqueues work, waited on by the next call when it uses another stream
+    cudaEvent_t order_ev = nullptr;
+    cudaStream_t order_stream = nullptr;
     std::mutex mu;
 };
 
@@ -162,10 +211,24 @@ int launch_bm25(const int32_t *doc_ids, const int32_t *tfs, int64_t n_post, floa
                 const float *doc_len, float avgdl, float k1, float b, float sign, float *out,
                 cudaStream_t st);
 int tensor_path_supported(const archi_store *s, int k);
+// Enqueues the whole tensor-path search of one batch (<= kTensorMaxBatch queries) on `st`, no host sync:
+// coarse launches, select + exact rescoring + proof, then the device-driven rescue of up to *max_sel_out
+// unproven queries.  The number of unproven queries lands in s->tws.h_verdict[0] behind s->tws.verdict_ev;
+// queries beyond max_sel (only possible for batches > 256) are returned as id -1 / score NaN and flagged in
+// s->tws.unverified.
 int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, const uint32_t *filter, int include_deleted,
                          float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st,
-                         int *n_unverified_host, int *unverified_host, double *coarse_ms);
+                         int *max_sel_out, double *coarse_ms);
+int launch_rescue(archi_store *s, const ScanArgs &a, const int *qsel_dev, const int *nsel_dev, int max_sel,
+                  float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st);
 void free_tensor_workspace(TensorWorkspace &w);
+void free_hybrid_workspace(HybridWorkspace &w);
+// One round of the posting-list hybrid search: n_slots <= 16 queries, n_pairs <= 96 (query, term) pairs starting at
+// pair0 of `t`, pair_slot[j] = query slot of pair j; dense_* = the queries' ordinary top-k (device).
+int launch_hybrid_sparse_round(archi_store *s, const float *q_dev, int n_slots, int k, const float *dense_scores,
+                               const int64_t *dense_ids, float w_sem, float w_bm25, float sign, const HybridTerms &t, int pair0,
+                               int n_pairs, const int *pair_slot, const uint32_t *filter, int include_deleted,
+                               float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st);
 int launch_merge_lists(const float *scores, const int64_t *ids, size_t scores_list_stride, size_t ids_list_stride,
                        int n_lists, int nq, int k, int larger_is_better, float *out_scores, int64_t *out_ids,
                        cudaStream_t st);

@@ -1,0 +1,444 @@
+// hybrid.cu -- hybrid BM25 + dense top-k without a dense per-row BM25 vector.
+//
+// Replaces hybrid_search's SQL (postgres_vectorstore.py:435-457):
+//     combined = (1.0 - (emb <op> q)) * w_sem + COALESCE(bm25, 0) * w_bm25   ORDER BY combined DESC LIMIT k
+// Rows without a lexical match have combined = w_sem * semantic, so (w_sem > 0, bm25 >= 0)
+//     exact fused top-k  =  top-k of ( dense top-k over ALL rows  U  exact combined score of S_q )
+// where S_q = rows that match at least one query term: a row outside S_q that is not in the dense top-k is
+// preceded by k rows whose combined score is at least their own dense score, ties included (lower id first).
+// Per batch of queries:
+//   1. the dense top-k of every query -- the ordinary search (tensor-core path for >= 2 queries);
+//   2. hyb_scatter_kernel   walks the posting lists of the query terms and accumulates BM25 per (query, row) into
+//                           a persistent, all-zero accumulator (64-bit fixed point: the sum does not depend on the
+//                           order of the atomics);
+//   3. hyb_fix_dense_kernel turns the dense scores into combined scores and drops dense rows that are in S_q;
+//   4. hyb_collect_kernel   walks the postings again: the first visitor of a row takes its BM25 sum (atomicExch
+//                           back to zero: the accumulator is clean again) and appends the row to the query's list;
+//   5. hyb_score_kernel     one warp per listed row: coalesced row load, exact fp32 dot, combined score,
+//                           warp-register top-k, block merge -> partial lists;
+//   6. hyb_merge_kernel     dense list + partial lists -> the k best (combined desc, id asc).
+// Work per query is O(postings of its terms) + one dense search instead of O(rows) extra traffic and a memset.
+// Queries whose terms match a large part of the corpus (stop-word-like terms) keep the dense-vector scan.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace archi {
+
+constexpr int kHybMaxPairs = kHybMaxPairsHost;    // (query, term) pairs per round (kernel-parameter space)
+constexpr int kHybMaxSlots = kHybMaxSlotsHost;    // queries per round (accumulator planes)
+constexpr int kHybCps = 8;          // CTAs scoring the candidates of one query
+constexpr float kFix = 4294967296.0f;           // 2^32: BM25 contributions are accumulated in 32.32 fixed point
+constexpr float kUnfix = 2.3283064365386963e-10f;
+
+struct HybPair {
+    long long start, end;   // posting range of the term
+    float idf;
+    int slot;               // query slot of this round
+};
+
+struct HybRound {
+    int n_pairs, n_slots;
+    long long total;                       // postings of all pairs
+    long long prefix[kHybMaxPairs + 1];    // exclusive prefix sums of the pairs' posting counts
+    HybPair pairs[kHybMaxPairs];
+    long long cand_off[kHybMaxSlots + 1];  // where each slot's candidate list starts
+};
+
+struct HybBm25 {
+    const int32_t *doc_ids;
+    const int32_t *tfs;
+    const float *doc_len;
+    float avgdl, k1, b;
+};
+
+__device__ __forceinline__ int hyb_pair_of(const long long *prefix, int n_pairs, long long p)
+{
+    int lo = 0, hi = n_pairs;             // largest j with prefix[j] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= p) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) hyb_scatter_kernel(const HybRound r, const HybBm25 bm, unsigned long long *acc,
+                                                          long long acc_stride)
+{
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < r.total; p += (long long)gridDim.x * blockDim.x) {
+        const int j = hyb_pair_of(r.prefix, r.n_pairs, p);
+        const long long off = r.pairs[j].start + (p - r.prefix[j]);
+        const int doc = bm.doc_ids[off];
+        const float tf = (float)bm.tfs[off];
+        const float denom = tf + bm.k1 * (1.0f - bm.b + bm.b * bm.doc_len[doc] / bm.avgdl);
+        const float c = r.pairs[j].idf * tf * (bm.k1 + 1.0f) / denom;       // same expression as bm25_term_kernel
+        atomicAdd(acc + (size_t)r.pairs[j].slot * acc_stride + doc, __float2ull_rn(c * kFix));
+    }
+}
+
+// dense (score, id) of the ordinary search -> (combined, local id); rows of S_q are dropped (id = INT_MAX)
+__global__ void hyb_fix_dense_kernel(const float *dense_scores, const long long *dense_ids, int k, int metric, float w_sem,
+                                     long long id_offset, const unsigned long long *acc, long long acc_stride,
+                                     float *comb_out, int *id_out)
+{
+    const int slot = blockIdx.x;
+    for (int rnk = threadIdx.x; rnk < k; rnk += blockDim.x) {
+        const long long gid = dense_ids[(size_t)slot * k + rnk];
+        float comb = -CUDART_INF_F;
+        int id = INT_MAX;
+        if (gid >= 0) {
+            const long long local = gid - id_offset;
+            if (acc[(size_t)slot * acc_stride + local] == 0ull) {
+                const float sc = dense_scores[(size_t)slot * k + rnk];
+                const float sem = metric == ARCHI_COSINE ? sc : 1.0f - sc;     // semantic = 1.0 - (emb <op> q), :441
+                comb = sem * w_sem;
+                id = (int)local;
+            }
+        }
+        comb_out[(size_t)slot * k + rnk] = comb;
+        id_out[(size_t)slot * k + rnk] = id;
+    }
+}
+
+__global__ void __launch_bounds__(256) hyb_collect_kernel(const HybRound r, const HybBm25 bm, unsigned long long *acc,
+                                                          long long acc_stride, int *cand_cnt, int *cand_doc, float *cand_bm)
+{
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < r.total; p += (long long)gridDim.x * blockDim.x) {
+        const int j = hyb_pair_of(r.prefix, r.n_pairs, p);
+        const long long off = r.pairs[j].start + (p - r.prefix[j]);
+        const int doc = bm.doc_ids[off];
+        const int slot = r.pairs[j].slot;
+        const unsigned long long sum = atomicExch(acc + (size_t)slot * acc_stride + doc, 0ull);
+        if (sum != 0ull) {          // first visitor of (slot, doc): owns the row, the accumulator is zero again
+            const int i = atomicAdd(cand_cnt + slot, 1);
+            cand_doc[r.cand_off[slot] + i] = doc;
+            cand_bm[r.cand_off[slot] + i] = __ull2float_rn(sum) * kUnfix;
+        }
+    }
+}
+
+struct HybScore {
+    const void *corpus;
+    int dtype, dim, ld, metric;
+    const float *norm2;
+    const uint32_t *alive;
+    const uint32_t *filter;
+    const float *queries;        // [n_slots, dim] of this round
+    float w_sem, w_bm25, sign;
+    int k;
+    const int *cand_cnt;
+    const int *cand_doc;
+    const float *cand_bm;
+    float *part_key;             // [n_slots][kHybCps][k]
+    int *part_id;
+};
+
+// Merge `nlists` sorted lists of 32*M entries staged in shared memory into `res` (same walk as scan.cu's block merge).
+template <int M>
+__device__ __forceinline__ void hyb_merge_staged(const float *skey, const int *sid, int nlists, int k, int lane, WarpTopK<M> &res)
+{
+    float tk = -CUDART_INF_F;
+    int ti = INT_MAX;
+    for (int l = 0; l < nlists; ++l) {
+#pragma unroll 1
+        for (int c = 0; c < M; ++c) {
+            const float ek = skey[l * 32 * M + c * 32 + lane];
+            const int ei = sid[l * 32 * M + c * 32 + lane];
+            unsigned cand = __ballot_sync(kFull, better(ek, ei, tk, ti));
+            if (cand == 0) break;
+            while (cand) {
+                const int src = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const float nk = __shfl_sync(kFull, ek, src);
+                const int ni = __shfl_sync(kFull, ei, src);
+                if (res.insert(nk, ni, k, lane)) res.threshold(k, tk, ti);
+            }
+        }
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const HybRound r)
+{
+    extern __shared__ __align__(16) unsigned char hsmem[];
+    float *sq = reinterpret_cast<float *>(hsmem);            // [ld] the slot's query, zero padded
+    __shared__ float s_qrn;
+    const int slot = blockIdx.x / kHybCps, cta = blockIdx.x % kHybCps;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int WARPS = 8;
+    for (int e = tid; e < p.ld; e += 256) sq[e] = e < p.dim ? p.queries[(size_t)slot * p.dim + e] : 0.f;
+    __syncthreads();
+    if (warp == 0) {
+        float ss = 0.f;
+        for (int e = lane; e < p.ld; e += 32) ss = fmaf(sq[e], sq[e], ss);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(kFull, ss, d);
+        if (lane == 0) s_qrn = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
+    }
+    __syncthreads();
+    const float qrn = s_qrn;
+    const int n = p.cand_cnt[slot];
+    const int *docs = p.cand_doc + r.cand_off[slot];
+    const float *bms = p.cand_bm + r.cand_off[slot];
+    const int vec = p.dtype == ARCHI_BF16 ? 8 : 4;
+    const int nvec = p.ld / vec;
+    const size_t row_bytes = (size_t)p.ld * (p.dtype == ARCHI_BF16 ? 2 : 4);
+    WarpTopK<M> list;
+    list.init();
+    for (int i = cta * WARPS + warp; i < n; i += kHybCps * WARPS) {
+        const int doc = docs[i];
+        bool ok = true;
+        if (p.alive) ok = ok && ((p.alive[doc >> 5] >> (doc & 31)) & 1u);
+        if (p.filter) ok = ok && ((p.filter[doc >> 5] >> (doc & 31)) & 1u);
+        if (!ok) continue;                                   // warp-uniform
+        const uint4 *rp = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(p.corpus) + (size_t)doc * row_bytes);
+        float acc = 0.f;
+        for (int v = lane; v < nvec; v += 32) {
+            const uint4 d = __ldg(rp + v);
+            const float *qq = sq + v * vec;
+            float x[8];
+            if (p.dtype == ARCHI_BF16) {
+                x[0] = __uint_as_float(d.x << 16); x[1] = __uint_as_float(d.x & 0xffff0000u);
+                x[2] = __uint_as_float(d.y << 16); x[3] = __uint_as_float(d.y & 0xffff0000u);
+                x[4] = __uint_as_float(d.z << 16); x[5] = __uint_as_float(d.z & 0xffff0000u);
+                x[6] = __uint_as_float(d.w << 16); x[7] = __uint_as_float(d.w & 0xffff0000u);
+            } else {
+                x[0] = __uint_as_float(d.x); x[1] = __uint_as_float(d.y);
+                x[2] = __uint_as_float(d.z); x[3] = __uint_as_float(d.w);
+                x[4] = x[5] = x[6] = x[7] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (e < vec) {
+                    if (p.metric == ARCHI_L2) {
+                        const float t = x[e] - qq[e];
+                        acc = fmaf(t, t, acc);
+                    } else {
+                        acc = fmaf(x[e], qq[e], acc);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
+        float sem;                                           // the scan kernel's hybrid key, term by term
+        if (p.metric == ARCHI_L2) {
+            sem = 1.0f - sqrtf(acc);
+        } else if (p.metric == ARCHI_COSINE) {
+            const float n2 = p.norm2[doc];
+            sem = fminf(1.0f, fmaxf(-1.0f, acc * qrn * (n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f)));
+        } else {
+            sem = 1.0f + acc;
+        }
+        const float key = fmaf(sem, p.w_sem, p.sign * bms[i] * p.w_bm25);
+        list.insert(key, doc, p.k, lane);
+    }
+    // block merge of the 8 warp lists
+    constexpr int LEN = 32 * M;
+    __syncthreads();
+    float *skey = reinterpret_cast<float *>(hsmem);
+    int *sid = reinterpret_cast<int *>(hsmem) + WARPS * LEN;
+#pragma unroll
+    for (int s = 0; s < M; ++s) {
+        skey[warp * LEN + s * 32 + lane] = list.key[s];
+        sid[warp * LEN + s * 32 + lane] = list.id[s];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        WarpTopK<M> res;
+        res.init();
+        hyb_merge_staged<M>(skey, sid, WARPS, p.k, lane, res);
+        float *ok_ = p.part_key + ((size_t)slot * kHybCps + cta) * p.k;
+        int *oi_ = p.part_id + ((size_t)slot * kHybCps + cta) * p.k;
+#pragma unroll
+        for (int s = 0; s < M; ++s) {
+            const int rank = s * 32 + lane;
+            if (rank < p.k) {
+                ok_[rank] = res.key[s];
+                oi_[rank] = res.id[s];
+            }
+        }
+    }
+}
+
+// one warp per query: dense list (combined) + kHybCps partial lists -> the k best
+template <int M>
+__global__ void __launch_bounds__(32) hyb_merge_kernel(const float *dense_comb, const int *dense_id, const float *part_key,
+                                                       const int *part_id, int k, long long id_offset, float *out_scores,
+                                                       long long *out_ids)
+{
+    const int slot = blockIdx.x, lane = threadIdx.x;
+    WarpTopK<M> res;
+    res.init();
+    auto feed = [&](const float *keys, const int *ids, int n) {
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const float ek = i < n ? keys[i] : -CUDART_INF_F;
+            const int ei = i < n ? ids[i] : INT_MAX;
+            unsigned cand = __ballot_sync(kFull, ei != INT_MAX);
+            while (cand) {
+                const int src = __ffs(cand) - 1;
+                cand &= cand - 1;
+                res.insert(__shfl_sync(kFull, ek, src), __shfl_sync(kFull, ei, src), k, lane);
+            }
+        }
+    };
+    feed(dense_comb + (size_t)slot * k, dense_id + (size_t)slot * k, k);
+    feed(part_key + (size_t)slot * kHybCps * k, part_id + (size_t)slot * kHybCps * k, kHybCps * k);
+#pragma unroll
+    for (int s = 0; s < M; ++s) {
+        const int rank = s * 32 + lane;
+        if (rank < k) {
+            const bool empty = res.id[s] == INT_MAX;
+            out_scores[(size_t)slot * k + rank] = empty ? CUDART_NAN_F : res.key[s];
+            out_ids[(size_t)slot * k + rank] = empty ? -1ll : (long long)res.id[s] + id_offset;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: one round of <= kHybMaxSlots queries whose terms are all "sparse"
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int hyb_ensure(T **ptr, size_t *cap, size_t need, bool zero, cudaStream_t st)
+{
+    if (*ptr && *cap >= need) return ARCHI_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    ARCHI_CUDA(cudaMalloc(ptr, need));
+    if (zero) ARCHI_CUDA(cudaMemsetAsync(*ptr, 0, need, st));
+    *cap = need;
+    return ARCHI_OK;
+}
+
+int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, dim] */, int n_slots, int k,
+                               const float *dense_scores, const int64_t *dense_ids, float w_sem, float w_bm25, float sign,
+                               const HybridTerms &t, int pair0, int n_pairs, const int *pair_slot,
+                               const uint32_t *filter, int include_deleted, float *out_scores, int64_t *out_ids,
+                               int64_t id_offset, cudaStream_t st)
+{
+    ARCHI_REQUIRE(n_slots >= 1 && n_slots <= kHybMaxSlots && n_pairs <= kHybMaxPairs, "hybrid: round too large");
+    ARCHI_REQUIRE(k >= 1 && k <= kMaxListK, "hybrid: k=%d out of range for the sparse path", k);
+    HybridWorkspace &w = s->hws;
+    HybRound r;
+    r.n_pairs = n_pairs;
+    r.n_slots = n_slots;
+    long long per_slot[kHybMaxSlots] = {0};
+    long long run = 0;
+    for (int j = 0; j < n_pairs; ++j) {
+        r.prefix[j] = run;
+        r.pairs[j].start = t.post_start[pair0 + j];
+        r.pairs[j].end = t.post_end[pair0 + j];
+        r.pairs[j].idf = t.idf[pair0 + j];
+        r.pairs[j].slot = pair_slot[j];
+        const long long n = r.pairs[j].end - r.pairs[j].start;
+        run += n;
+        per_slot[pair_slot[j]] += n;
+    }
+    r.prefix[n_pairs] = run;
+    r.total = run;
+    long long off = 0;
+    for (int sl = 0; sl < n_slots; ++sl) {
+        r.cand_off[sl] = off;
+        off += per_slot[sl];
+    }
+    r.cand_off[n_slots] = off;
+
+    int rc;
+    // the accumulator planes are all-zero between calls (hyb_collect_kernel restores every entry it read)
+    const size_t acc_need = (size_t)kHybMaxSlots * (size_t)s->capacity * sizeof(unsigned long long);
+    if (!w.acc || w.acc_bytes < acc_need || w.acc_dirty) {
+        if (w.acc && w.acc_bytes >= acc_need) ARCHI_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
+        else if ((rc = hyb_ensure(&w.acc, &w.acc_bytes, acc_need, true, st)) != ARCHI_OK) return rc;
+        w.acc_dirty = false;
+    }
+    const size_t cand_need = (size_t)(off > 0 ? off : 1);
+    if ((rc = hyb_ensure(&w.cand_doc, &w.cand_doc_bytes, cand_need * sizeof(int), false, st)) != ARCHI_OK) return rc;
+    if ((rc = hyb_ensure(&w.cand_bm, &w.cand_bm_bytes, cand_need * sizeof(float), false, st)) != ARCHI_OK) return rc;
+    if ((rc = hyb_ensure(&w.cand_cnt, &w.cand_cnt_bytes, kHybMaxSlots * sizeof(int), false, st)) != ARCHI_OK) return rc;
+    const size_t list_need = (size_t)kHybMaxSlots * (kHybCps + 1) * kMaxListK;
+    if ((rc = hyb_ensure(&w.part_key, &w.part_key_bytes, list_need * sizeof(float), false, st)) != ARCHI_OK) return rc;
+    if ((rc = hyb_ensure(&w.part_id, &w.part_id_bytes, list_need * sizeof(int), false, st)) != ARCHI_OK) return rc;
+    float *dense_comb = w.part_key + (size_t)kHybMaxSlots * kHybCps * kMaxListK;
+    int *dense_id = w.part_id + (size_t)kHybMaxSlots * kHybCps * kMaxListK;
+
+    HybBm25 bm;
+    bm.doc_ids = t.doc_ids_dev;
+    bm.tfs = t.tfs_dev;
+    bm.doc_len = t.doc_len_dev;
+    bm.avgdl = t.avgdl;
+    bm.k1 = t.k1;
+    bm.b = t.b;
+    const long long acc_stride = s->capacity;
+    w.acc_dirty = true;          // until hyb_collect_kernel has been enqueued
+    ARCHI_CUDA(cudaMemsetAsync(w.cand_cnt, 0, kHybMaxSlots * sizeof(int), st));
+    if (r.total > 0) {
+        long long blocks = (r.total + 255) / 256;
+        if (blocks > (long long)s->sm_count * 8) blocks = (long long)s->sm_count * 8;
+        hyb_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(r, bm, w.acc, acc_stride);
+        ARCHI_CHECK_LAUNCH();
+    }
+    hyb_fix_dense_kernel<<<n_slots, 128, 0, st>>>(dense_scores, reinterpret_cast<const long long *>(dense_ids), k, s->metric, w_sem,
+                                                  id_offset, w.acc, acc_stride, dense_comb, dense_id);
+    ARCHI_CHECK_LAUNCH();
+    if (r.total > 0) {
+        long long blocks = (r.total + 255) / 256;
+        if (blocks > (long long)s->sm_count * 8) blocks = (long long)s->sm_count * 8;
+        hyb_collect_kernel<<<(unsigned)blocks, 256, 0, st>>>(r, bm, w.acc, acc_stride, w.cand_cnt, w.cand_doc, w.cand_bm);
+        ARCHI_CHECK_LAUNCH();
+    }
+    w.acc_dirty = false;
+    HybScore sp;
+    sp.corpus = s->data;
+    sp.dtype = s->dtype;
+    sp.dim = s->dim;
+    sp.ld = s->ld;
+    sp.metric = s->metric;
+    sp.norm2 = s->norm2;
+    sp.alive = include_deleted ? nullptr : s->alive;
+    sp.filter = filter;
+    sp.queries = q_dev;
+    sp.w_sem = w_sem;
+    sp.w_bm25 = w_bm25;
+    sp.sign = sign;
+    sp.k = k;
+    sp.cand_cnt = w.cand_cnt;
+    sp.cand_doc = w.cand_doc;
+    sp.cand_bm = w.cand_bm;
+    sp.part_key = w.part_key;
+    sp.part_id = w.part_id;
+    const int M = k <= 32 ? 1 : 4;
+    const size_t q_bytes = (size_t)s->ld * sizeof(float);
+    const size_t m_bytes = (size_t)8 * 32 * M * 8;
+    const size_t smem = q_bytes > m_bytes ? q_bytes : m_bytes;
+    if (M == 1) {
+        if (smem > 40 * 1024) ARCHI_CUDA(cudaFuncSetAttribute((const void *)hyb_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hyb_score_kernel<1><<<n_slots * kHybCps, 256, smem, st>>>(sp, r);
+    } else {
+        if (smem > 40 * 1024) ARCHI_CUDA(cudaFuncSetAttribute((const void *)hyb_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hyb_score_kernel<4><<<n_slots * kHybCps, 256, smem, st>>>(sp, r);
+    }
+    ARCHI_CHECK_LAUNCH();
+    if (M == 1)
+        hyb_merge_kernel<1><<<n_slots, 32, 0, st>>>(dense_comb, dense_id, w.part_key, w.part_id, k, id_offset, out_scores,
+                                                    reinterpret_cast<long long *>(out_ids));
+    else
+        hyb_merge_kernel<4><<<n_slots, 32, 0, st>>>(dense_comb, dense_id, w.part_key, w.part_id, k, id_offset, out_scores,
+                                                    reinterpret_cast<long long *>(out_ids));
+    ARCHI_CHECK_LAUNCH();
+    return ARCHI_OK;
+}
+
+void free_hybrid_workspace(HybridWorkspace &w)
+{
+    void *ptrs[] = {w.acc, w.cand_doc, w.cand_bm, w.cand_cnt, w.part_key, w.part_id, w.bias, w.dense_scores, w.dense_ids};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    w = HybridWorkspace();
+}
+
+}  // namespace archi

@@ -34,6 +34,14 @@ struct ScanParams {
     const int *cursor_id;
     float *part_key;
     int *part_id;
+    // rescue mode (RESCUE kernels only): the queries to scan are named by a DEVICE list, so that the launch
+    // needs no host knowledge of how many there are: slots [0, min(*nsel, max_sel)) of qsel are row indices
+    // into `queries`; the kernel takes them QB at a time and writes the partial lists of pass j at
+    // part_* + j * pass_stride.  *nsel == 0 makes the launch a no-op.
+    const int *qsel;
+    const int *nsel;
+    int max_sel;
+    long long pass_stride;
 };
 
 template <typename T>
@@ -130,7 +138,7 @@ __device__ __forceinline__ void merge_staged(const float *skey, const int *sid, 
     }
 }
 
-template <typename T, int QB, int R, int M, bool L2>
+template <typename T, int QB, int R, int M, bool L2, bool RESCUE = false>
 __global__ void __launch_bounds__(kScanThreads, (QB >= 8 ? 1 : 2)) scan_topk_kernel(const ScanParams p)
 {
     constexpr int VEC = Elt<T>::VEC;
@@ -148,11 +156,24 @@ __global__ void __launch_bounds__(kScanThreads, (QB >= 8 ? 1 : 2)) scan_topk_ker
     const int J = (nvec + 31) >> 5;      // lane-wide load groups per row
     const int qstride = J * 32 * VEC;    // floats per staged query (zero padded)
 
+    int n_sel = p.nqb;
+    if constexpr (RESCUE) {
+        n_sel = *p.nsel;
+        if (n_sel > p.max_sel) n_sel = p.max_sel;
+    }
+    // one iteration unless RESCUE: the selected queries are taken QB at a time
+#pragma unroll 1
+    for (int q0 = 0; q0 < n_sel; q0 += QB) {
+    const int nqb = n_sel - q0 < QB ? n_sel - q0 : QB;
+    float *const part_key = p.part_key + (RESCUE ? (q0 / QB) * p.pass_stride : 0);
+    int *const part_id = p.part_id + (RESCUE ? (q0 / QB) * p.pass_stride : 0);
+
     // ---- stage the queries in shared memory (bf16 rows: split into lo/hi float4 planes so that
     //      both LDS.128 of a lane are conflict-free) -------------------------------------------
     for (int idx = tid; idx < QB * qstride; idx += kScanThreads) {
         const int q = idx / qstride, e = idx - q * qstride;
-        const float val = (q < p.nqb && e < p.dim) ? p.queries[(size_t)q * p.dim + e] : 0.f;
+        const size_t qrow = RESCUE ? (size_t)(q < nqb ? p.qsel[q0 + q] : 0) : (size_t)q;
+        const float val = (q < nqb && e < p.dim) ? p.queries[qrow * p.dim + e] : 0.f;
         int pos = e;
         if (VEC == 8) {
             const int v = e >> 3, c = e & 7;
@@ -171,7 +192,7 @@ __global__ void __launch_bounds__(kScanThreads, (QB >= 8 ? 1 : 2)) scan_topk_ker
         for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(kFull, ss, d);
         if (lane == 0) {
             s_qrn[q] = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
-            const bool cur = p.cursor_key != nullptr && q < p.nqb;
+            const bool cur = p.cursor_key != nullptr && q < nqb;
             s_ckey[q] = cur ? p.cursor_key[q] : CUDART_INF_F;
             s_cid[q] = cur ? p.cursor_id[q] : -1;
         }
@@ -181,7 +202,7 @@ __global__ void __launch_bounds__(kScanThreads, (QB >= 8 ? 1 : 2)) scan_topk_ker
     // ---- per-lane role after the transposed reduction: value index = lane >> SH -------------
     const int my_idx = lane >> SH;
     const int my_r = my_idx / QB, my_q = my_idx % QB;
-    const bool owner = (lane & ((1 << SH) - 1)) == 0 && my_q < p.nqb;
+    const bool owner = (lane & ((1 << SH) - 1)) == 0 && my_q < nqb;
     const float my_qrn = s_qrn[my_q];
     const float my_ckey = s_ckey[my_q];
     const int my_cid = s_cid[my_q];
@@ -311,12 +332,12 @@ __global__ void __launch_bounds__(kScanThreads, (QB >= 8 ? 1 : 2)) scan_topk_ker
         }
     }
     __syncthreads();
-    for (int q = warp; q < p.nqb; q += WARPS) {
+    for (int q = warp; q < nqb; q += WARPS) {
         WarpTopK<M> res;
         res.init();
         merge_staged<M>(skey + q * WARPS * LEN, sid + q * WARPS * LEN, WARPS, p.k, lane, res);
-        float *ok_ = p.part_key + ((size_t)blockIdx.x * kMaxQB + q) * kMaxListK;
-        int *oi_ = p.part_id + ((size_t)blockIdx.x * kMaxQB + q) * kMaxListK;
+        float *ok_ = part_key + ((size_t)blockIdx.x * kMaxQB + q) * kMaxListK;
+        int *oi_ = part_id + ((size_t)blockIdx.x * kMaxQB + q) * kMaxListK;
 #pragma unroll
         for (int s = 0; s < M; ++s) {
             const int rank = s * 32 + lane;
@@ -325,6 +346,8 @@ __global__ void __launch_bounds__(kScanThreads, (QB >= 8 ? 1 : 2)) scan_topk_ker
                 oi_[rank] = res.id[s];
             }
         }
+    }
+    __syncthreads();      // the staged lists share the query area of the next iteration
     }
 }
 
@@ -343,6 +366,11 @@ struct FinalizeParams {
     long long id_offset;
     float *cursor_key_out;
     int *cursor_id_out;
+    // rescue mode: CTA i finalises slot i of the device list (see ScanParams), writes output row qsel[i]
+    const int *qsel;
+    const int *nsel;
+    int max_sel;
+    long long pass_stride;
 };
 
 // Radix select instead of list insertion: the grid*k candidate keys are staged in shared memory,
@@ -361,11 +389,21 @@ __global__ void __launch_bounds__(kScanThreads) scan_finalize_kernel(const Final
     __shared__ int s_sid[kFinKeep];
     __shared__ int s_eid[kFinEq];
     const int tid = threadIdx.x;
-    const int q = blockIdx.x;
+    int q = blockIdx.x;            // which partial list of each CTA
+    int out_row = blockIdx.x;      // which row of the outputs
+    size_t pass_off = 0;
+    if (p.qsel) {
+        int n_sel = *p.nsel;
+        if (n_sel > p.max_sel) n_sel = p.max_sel;
+        if ((int)blockIdx.x >= n_sel) return;
+        out_row = p.qsel[blockIdx.x];
+        q = blockIdx.x % kMaxQB;
+        pass_off = (size_t)(blockIdx.x / kMaxQB) * (size_t)p.pass_stride;
+    }
     const int total = p.grid * p.k;
     auto slot_of = [&](int i) {
         const int b = i / p.k, r = i - b * p.k;
-        return ((size_t)b * kMaxQB + q) * kMaxListK + r;
+        return pass_off + ((size_t)b * kMaxQB + q) * kMaxListK + r;
     };
     if (tid == 0) {
         s_nk = 0;
@@ -418,7 +456,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_finalize_kernel(const Final
             else if (p.hybrid || p.metric == ARCHI_COSINE) score = key;
             else if (p.metric == ARCHI_L2) score = sqrtf(fmaxf(-key, 0.f));
             else score = -key;
-            const size_t o = (size_t)q * p.k_total + p.col0 + rank;
+            const size_t o = (size_t)out_row * p.k_total + p.col0 + rank;
             p.out_scores[o] = score;
             p.out_ids[o] = empty ? -1ll : (long long)id + p.id_offset;
             if (rank == p.k - 1 && p.cursor_key_out) {
@@ -426,7 +464,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_finalize_kernel(const Final
                 p.cursor_id_out[q] = id;
             }
         } else {
-            const size_t o = (size_t)q * p.k_total + p.col0 + i;
+            const size_t o = (size_t)out_row * p.k_total + p.col0 + i;
             p.out_scores[o] = CUDART_NAN_F;
             p.out_ids[o] = -1ll;
             if (i == p.k - 1 && p.cursor_key_out) {
@@ -524,9 +562,111 @@ int launch_scan(archi_store *s, const ScanArgs &a, cudaStream_t st, int *grid_ou
     p.cursor_id = a.cursor_id;
     p.part_key = s->ws.part_key;
     p.part_id = s->ws.part_id;
+    p.qsel = nullptr;
+    p.nsel = nullptr;
+    p.max_sel = 0;
+    p.pass_stride = 0;
     fn<<<(unsigned)grid, kScanThreads, smem, st>>>(p);
     ARCHI_CHECK_LAUNCH();
     *grid_out = (int)grid;
+    return ARCHI_OK;
+}
+
+template <typename T>
+static scan_fn_t pick_rescue(int M, bool l2)
+{
+    if (M == 1) return l2 ? scan_topk_kernel<T, 8, 4, 1, true, true> : scan_topk_kernel<T, 8, 4, 1, false, true>;
+    return l2 ? scan_topk_kernel<T, 8, 4, 4, true, true> : scan_topk_kernel<T, 8, 4, 4, false, true>;
+}
+
+// Device-driven exact re-scan of the queries named by a device list (the tensor path's unproven queries):
+// two launches that cost a few microseconds when the list is empty and need no host round trip.
+int launch_rescue(archi_store *s, const ScanArgs &a, const int *qsel_dev, const int *nsel_dev, int max_sel,
+                  float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st)
+{
+    ARCHI_REQUIRE(a.k >= 1 && a.k <= kMaxListK, "rescue: k=%d out of range", a.k);
+    ARCHI_REQUIRE(max_sel >= 1 && max_sel % kMaxQB == 0, "rescue: max_sel=%d must be a positive multiple of %d", max_sel, kMaxQB);
+    constexpr int QB = 8, R = 4;
+    const int M = a.k <= 32 ? 1 : 4;
+    const bool l2 = a.metric == ARCHI_L2;
+    const int VEC = a.dtype == ARCHI_BF16 ? 8 : 4;
+    const int J = (a.ld / VEC + 31) / 32;
+    const size_t q_bytes = (size_t)QB * J * 32 * VEC * sizeof(float);
+    const size_t m_bytes = (size_t)(kScanThreads / 32) * QB * 32 * M * 8;
+    const size_t smem = q_bytes > m_bytes ? q_bytes : m_bytes;
+    ARCHI_REQUIRE(smem <= 200 * 1024, "rescue: dim=%d needs %zu B of shared memory per CTA", a.dim, smem);
+    scan_fn_t fn = a.dtype == ARCHI_BF16 ? pick_rescue<__nv_bfloat16>(M, l2) : pick_rescue<float>(M, l2);
+    ARCHI_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ngroups = (a.n + R - 1) / R;
+    long long grid = s->sm_count;      // one CTA per SM (launch bounds of the QB = 8 kernels)
+    const long long want = (ngroups + (kScanThreads / 32) - 1) / (kScanThreads / 32);
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    const int passes = max_sel / kMaxQB;
+    const long long pass_stride = grid * kMaxQB * kMaxListK;
+    Workspace &w = s->ws;
+    if (w.resc_elems < pass_stride * passes) {
+        if (w.resc_key) cudaFree(w.resc_key);
+        if (w.resc_id) cudaFree(w.resc_id);
+        w.resc_key = nullptr;
+        w.resc_id = nullptr;
+        w.resc_elems = 0;
+        ARCHI_CUDA(cudaMalloc(&w.resc_key, (size_t)pass_stride * passes * sizeof(float)));
+        ARCHI_CUDA(cudaMalloc(&w.resc_id, (size_t)pass_stride * passes * sizeof(int)));
+        w.resc_elems = pass_stride * passes;
+    }
+    ScanParams p;
+    p.corpus = a.corpus;
+    p.n = a.n;
+    p.dim = a.dim;
+    p.ld = a.ld;
+    p.metric = a.metric;
+    p.queries = a.queries;
+    p.nqb = 0;
+    p.k = a.k;
+    p.norm2 = a.norm2;
+    p.alive = a.alive;
+    p.filter = a.filter;
+    p.hybrid = 0;
+    p.bias = nullptr;
+    p.bias_stride = 0;
+    p.w_sem = 1.f;
+    p.w_bias = 0.f;
+    p.cursor_key = nullptr;
+    p.cursor_id = nullptr;
+    p.part_key = w.resc_key;
+    p.part_id = w.resc_id;
+    p.qsel = qsel_dev;
+    p.nsel = nsel_dev;
+    p.max_sel = max_sel;
+    p.pass_stride = pass_stride;
+    fn<<<(unsigned)grid, kScanThreads, smem, st>>>(p);
+    ARCHI_CHECK_LAUNCH();
+
+    FinalizeParams f;
+    f.part_key = w.resc_key;
+    f.part_id = w.resc_id;
+    f.grid = (int)grid;
+    f.k = a.k;
+    f.k_total = a.k;
+    f.col0 = 0;
+    f.metric = a.metric;
+    f.hybrid = 0;
+    f.out_scores = out_scores;
+    f.out_ids = reinterpret_cast<long long *>(out_ids);
+    f.id_offset = id_offset;
+    f.cursor_key_out = nullptr;
+    f.cursor_id_out = nullptr;
+    f.qsel = qsel_dev;
+    f.nsel = nsel_dev;
+    f.max_sel = max_sel;
+    f.pass_stride = pass_stride;
+    const size_t fsmem = (size_t)grid * a.k * sizeof(uint32_t);
+    ARCHI_REQUIRE(fsmem <= 200 * 1024, "rescue: %zu B of candidate keys do not fit in shared memory", fsmem);
+    if (fsmem > 40 * 1024)
+        ARCHI_CUDA(cudaFuncSetAttribute((const void *)scan_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    scan_finalize_kernel<<<max_sel, kScanThreads, fsmem, st>>>(f);
+    ARCHI_CHECK_LAUNCH();
     return ARCHI_OK;
 }
 
@@ -548,6 +688,10 @@ int launch_scan_finalize(archi_store *s, const ScanArgs &a, int grid, int k_tota
     p.id_offset = id_offset;
     p.cursor_key_out = cursor_key_out;
     p.cursor_id_out = cursor_id_out;
+    p.qsel = nullptr;
+    p.nsel = nullptr;
+    p.max_sel = 0;
+    p.pass_stride = 0;
     const size_t smem = (size_t)grid * a.k * sizeof(uint32_t);
     ARCHI_REQUIRE(smem <= 200 * 1024, "scan_finalize: %zu B of candidate keys do not fit in shared memory", smem);
     if (smem > 40 * 1024)

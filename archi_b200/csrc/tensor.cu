@@ -776,7 +776,12 @@ tc_coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 // 4. select k' best coarse candidates, rescore exactly, prove, write the outputs
 // ---------------------------------------------------------------------------------------------
 constexpr int SEL_THREADS = 256;
-constexpr int KEPT_MAX = 320;
+constexpr int KEPT_MAX = 448;
+// Margin scheme: thresholds and the final selection are placed `kMarginMult * eps_q` BELOW the k-th best coarse
+// key they are derived from.  The k rows with coarse key >= c_k have exact keys >= c_k - eps, every row that was
+// rejected or not rescored has coarse key <= c_k - 2.1 eps, hence exact key <= c_k - 1.1 eps < e_k: the proof
+// holds by construction unless more than KEPT_MAX rows crowd into that window (duplicates).
+constexpr float kMarginMult = 2.1f;
 
 struct SelectParams {
     const void *corpus;
@@ -788,12 +793,16 @@ struct SelectParams {
     const int *cand_cnt;
     const uint32_t *thr_g;
     int qt_count, ngroups, cap;
-    int k, kprime;
+    int k, kprime;            // kprime: rank the selection threshold is taken at (k itself with the margin scheme)
+    int margin;               // 1: rescore everything within kMarginMult * eps of the k-th best coarse key
     float *out_scores;
     long long *out_ids;
     long long id_offset;
     int *unverified;          // [nq] flag
     int *n_unverified;        // [1] counter
+    int *unv_list;            // [max_sel] the unproven queries, in arrival order (input of the rescue scan)
+    int max_sel;              // unproven queries beyond this many are returned as id -1 / score NaN
+    int *sticky;              // [1] running count of such queries (never reset)
 };
 
 __device__ __forceinline__ float row_elem(const void *corpus, int dtype, size_t idx)
@@ -818,7 +827,7 @@ __device__ __forceinline__ size_t sel_list_base(const SelCommon &c, int l, int q
     return ((size_t)((l >> 1) * c.qt_count + qt)) * 2 + (l & 1);
 }
 
-constexpr int SEL_STAGE = 8192;   // keys staged in shared memory for the radix passes when they fit
+constexpr int SEL_STAGE = 7680;   // keys staged in shared memory for the radix passes when they fit
 
 constexpr int SEL_LISTS_MAX = 320;   // 2 * ngroups <= 296
 
@@ -955,6 +964,8 @@ __device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int 
 struct ThresholdParams {
     SelCommon c;
     uint32_t *thr_g;
+    const QInfo *qinfo;
+    int margin;
 };
 
 __global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const ThresholdParams p)
@@ -966,7 +977,10 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const Thresho
     __shared__ uint32_t s_stage[SEL_STAGE];
     int total;
     const uint32_t T = sel_radix_threshold(p.c, blockIdx.x, s_cnt, s_off, s_hist, s_misc, s_stage, total);
-    if (threadIdx.x == 0 && total > p.c.kprime) atomicMax(p.thr_g + blockIdx.x, T);
+    if (threadIdx.x == 0 && total > p.c.kprime) {
+        const uint32_t Tm = p.margin ? fmap(funmap(T) - kMarginMult * p.qinfo[blockIdx.x].eps) : T;
+        atomicMax(p.thr_g + blockIdx.x, Tm);
+    }
 }
 
 // After a probe launch: per query, the kprime-th largest chunk maximum over all lists becomes the
@@ -975,6 +989,8 @@ struct MaxThrParams {
     const float *chunkmax;
     int qt_count, ngroups, cm_slots, used_slots, kprime, nq;
     uint32_t *thr_g;
+    const QInfo *qinfo;
+    int margin;
 };
 
 constexpr int MAXTHR_Q = 8;            // queries per CTA of tc_maxima_threshold_kernel: one warp each for the selection
@@ -1020,7 +1036,7 @@ __global__ void __launch_bounds__(MAXTHR_THREADS) tc_maxima_threshold_kernel(con
     valid = __reduce_add_sync(kFull, valid);
     if (valid < p.kprime) return;                    // fewer live rows than kprime seen: no threshold yet
     const uint32_t T = warp_radix_kth(keys, total, p.kprime, s_hist[warp], lane);
-    if (lane == 0) atomicMax(p.thr_g + q, T);
+    if (lane == 0) atomicMax(p.thr_g + q, p.margin ? fmap(funmap(T) - kMarginMult * p.qinfo[q].eps) : T);
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
@@ -1050,7 +1066,9 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     for (int e = tid; e < p.ld; e += SEL_THREADS) s_q[e] = e < p.dim ? p.queries[(size_t)q * p.dim + e] : 0.f;
     const QInfo qi = p.qinfo[q];
     int total;
-    const uint32_t T = sel_radix_threshold(sc, q, s_cnt, s_off, s_hist, s_misc, s_stage, total);
+    uint32_t T = sel_radix_threshold(sc, q, s_cnt, s_off, s_hist, s_misc, s_stage, total);
+    // margin scheme: T is the k-th best coarse key c_k; everything down to c_k - kMarginMult * eps is rescored
+    if (p.margin && total > p.kprime) T = fmap(funmap(T) - kMarginMult * qi.eps);
     __syncthreads();
 
     // gather the survivors (key >= T)
@@ -1173,7 +1191,11 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     }
     // proof: every row outside the kept set has coarse key <= Tv, hence exact key <= Tv + eps
     __shared__ float s_ek;
-    if (tid == 0) s_ek = -CUDART_INF_F;
+    __shared__ int s_poison;
+    if (tid == 0) {
+        s_ek = -CUDART_INF_F;
+        s_poison = 0;
+    }
     __syncthreads();
     if (ek > -CUDART_INF_F) s_ek = ek;               // exactly one thread holds rank k-1
     __syncthreads();
@@ -1183,8 +1205,21 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
         bool ok = !overflow;
         if (Tv > -CUDART_INF_F) ok = ok && nk >= p.k && s_ek > Tv + qi.eps;
         if (!ok) {
+            // unproven: queue the query for the exact re-scan that follows on the same stream
             p.unverified[q] = 1;
-            atomicAdd(p.n_unverified, 1);
+            const int slot = atomicAdd(p.n_unverified, 1);
+            if (slot < p.max_sel) p.unv_list[slot] = q;
+            else {
+                s_poison = 1;                        // no room in the rescue list: never return an unproven row
+                atomicAdd(p.sticky, 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (s_poison) {
+        for (int r = tid; r < p.k; r += SEL_THREADS) {
+            p.out_scores[(size_t)q * p.k + r] = CUDART_NAN_F;
+            p.out_ids[(size_t)q * p.k + r] = -1;
         }
     }
 }
@@ -1233,6 +1268,50 @@ static int make_tmap(CUtensorMap *map, const void *base, int is_f32, long long r
     return ARCHI_OK;
 }
 
+// The descriptor of a matrix is rebuilt only when its base, shape or box changes (cuTensorMapEncodeTiled costs
+// microseconds of host time per call, which is all a small shard's search has).
+static int cached_tmap(unsigned char *slot, const void **c_base, long long *c_rows, int *c_ld, int *c_f32, int *c_box,
+                       const void *base, int is_f32, long long rows, int ld, int box_rows)
+{
+    if (*c_base == base && *c_rows == rows && *c_ld == ld && *c_f32 == is_f32 && (!c_box || *c_box == box_rows))
+        return ARCHI_OK;
+    int rc = make_tmap(reinterpret_cast<CUtensorMap *>(slot), base, is_f32, rows, ld, box_rows);
+    if (rc != ARCHI_OK) {
+        *c_base = nullptr;
+        return rc;
+    }
+    *c_base = base;
+    *c_rows = rows;
+    *c_ld = ld;
+    *c_f32 = is_f32;
+    if (c_box) *c_box = box_rows;
+    return ARCHI_OK;
+}
+
+// cudaFuncSetAttribute once per kernel and size (a driver call per search otherwise)
+static int set_dyn_smem_once(const void *fn, int bytes)
+{
+    static std::mutex mu;
+    static const void *fns[32];
+    static int sizes[32];
+    static int n = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n; ++i)
+        if (fns[i] == fn) {
+            if (sizes[i] >= bytes) return ARCHI_OK;
+            ARCHI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            sizes[i] = bytes;
+            return ARCHI_OK;
+        }
+    ARCHI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (n < 32) {
+        fns[n] = fn;
+        sizes[n] = bytes;
+        ++n;
+    }
+    return ARCHI_OK;
+}
+
 template <typename T>
 static int ensure_buf(T **ptr, size_t *cap_bytes, size_t need_bytes)
 {
@@ -1253,7 +1332,7 @@ int tensor_path_supported(const archi_store *s, int k)
 
 int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, const uint32_t *filter, int include_deleted,
                          float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st,
-                         int *n_unverified_host, int *unverified_host /* [nq] */, double *coarse_ms)
+                         int *max_sel_out, double *coarse_ms)
 {
     using namespace tc;
     TensorWorkspace &w = s->tws;
@@ -1274,6 +1353,8 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     const int nq_pad = qt_count * BM;
     int kprime = k <= 10 ? 32 : round_up(2 * k + 12, 32);
     if (kprime > 256) kprime = 256;
+    // ARCHI_TC_MARGIN=0 restores the older scheme (thresholds at the k'-th best key, no margin)
+    static const int margin = getenv("ARCHI_TC_MARGIN") ? atoi(getenv("ARCHI_TC_MARGIN")) : 1;
     // buffer capacity: after a compaction (kprime entries) a buffer absorbs cap - BN - kprime more
     // candidates before the next one; a whole tile (BN) always fits
     const int cap = 1024;
@@ -1290,6 +1371,16 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     if ((rc = ensure_buf(&w.qinfo, &w.qinfo_bytes, (size_t)nq_pad * sizeof(QInfo))) != ARCHI_OK) return rc;
     if ((rc = ensure_buf(&w.thr_g, &w.thr_bytes, (size_t)nq_pad * 4)) != ARCHI_OK) return rc;
     if ((rc = ensure_buf(&w.unverified, &w.unv_bytes, (size_t)(nq_pad + 1) * 4)) != ARCHI_OK) return rc;
+    // every query of a batch of <= 256 can be rescued; larger batches rescue up to 256 of theirs
+    const int max_sel = nq <= 256 ? round_up(nq, kMaxQB) : 256;
+    if ((rc = ensure_buf(&w.unv_list, &w.unv_list_bytes, (size_t)256 * 4)) != ARCHI_OK) return rc;
+    if (!w.h_verdict) {
+        ARCHI_CUDA(cudaHostAlloc(&w.h_verdict, 64 * sizeof(int), cudaHostAllocDefault));
+        ARCHI_CUDA(cudaEventCreateWithFlags(&w.verdict_ev, cudaEventDisableTiming));
+        ARCHI_CUDA(cudaMalloc(&w.sticky_dev, sizeof(int)));
+        ARCHI_CUDA(cudaMemsetAsync(w.sticky_dev, 0, sizeof(int), st));
+    }
+    w.unv_count = w.unverified + nq_pad;
     if ((rc = ensure_buf(&w.cand, &w.cand_bytes, (size_t)grid * 2 * BM * cap * sizeof(uint2))) != ARCHI_OK) return rc;
     if ((rc = ensure_buf(&w.cand_cnt, &w.cnt_bytes, (size_t)grid * 2 * BM * 4)) != ARCHI_OK) return rc;
     {
@@ -1380,11 +1471,15 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     ARCHI_CHECK_LAUNCH();
 
     // ---- 3. coarse scorer ----
-    CUtensorMap tmap_q, tmap_c;
-    if ((rc = make_tmap(&tmap_q, w.qstage, tf32, nq_pad, ldq, BM)) != ARCHI_OK) return rc;
-    if ((rc = make_tmap(&tmap_c, use_shadow ? w.shadow : s->data, tf32, s->rows, use_shadow ? ld_sh : s->ld,
-                        pair ? BN / 2 : BN)) != ARCHI_OK)
+    if ((rc = cached_tmap(w.tmap_q, &w.tmq_base, &w.tmq_rows, &w.tmq_ld, &w.tmq_f32, nullptr, w.qstage, tf32, nq_pad, ldq,
+                          BM)) != ARCHI_OK)
         return rc;
+    if ((rc = cached_tmap(w.tmap_c, &w.tmc_base, &w.tmc_rows, &w.tmc_ld, &w.tmc_f32, &w.tmc_box,
+                          use_shadow ? w.shadow : s->data, tf32, s->rows, use_shadow ? ld_sh : s->ld,
+                          pair ? BN / 2 : BN)) != ARCHI_OK)
+        return rc;
+    const CUtensorMap &tmap_q = *reinterpret_cast<const CUtensorMap *>(w.tmap_q);
+    const CUtensorMap &tmap_c = *reinterpret_cast<const CUtensorMap *>(w.tmap_c);
     CoarseParams cp;
     cp.n = s->rows;
     cp.n_ctiles = n_ctiles;
@@ -1422,7 +1517,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
                           : (raw ? tc_coarse_pair_kernel<false, true> : tc_coarse_pair_kernel<false, false>);
     else kern = tf32 ? (raw ? tc_coarse_kernel<true, true> : tc_coarse_kernel<true, false>)
                      : (raw ? tc_coarse_kernel<false, true> : tc_coarse_kernel<false, false>);
-    ARCHI_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    if ((rc = set_dyn_smem_once((const void *)kern, SMEM_BYTES)) != ARCHI_OK) return rc;
     // Thresholds local to one (CTA, epilogue group) only ever see 1/(2*ngroups) of the rows, so most of
     // a plain run would be spent storing candidates that a global view rejects.  The scan therefore
     // starts from ONE shared threshold per query, derived from a small sample of the corpus.
@@ -1462,11 +1557,13 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         mp.ngroups = ngroups;
         mp.cm_slots = cm_slots;
         mp.used_slots = per_vcta * 8;
-        mp.kprime = kprime;
+        mp.kprime = margin ? k : kprime;
         mp.nq = nq;
         mp.thr_g = w.thr_g;
+        mp.qinfo = reinterpret_cast<const QInfo *>(w.qinfo);
+        mp.margin = margin;
         const size_t mt_smem = (size_t)MAXTHR_Q * (round_up(nlists * mp.used_slots, 32) + 4) * 4;
-        ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_maxima_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mt_smem));
+        if ((rc = set_dyn_smem_once((const void *)tc_maxima_threshold_kernel, (int)mt_smem)) != ARCHI_OK) return rc;
         tc_maxima_threshold_kernel<<<(nq + MAXTHR_Q - 1) / MAXTHR_Q, MAXTHR_THREADS, mt_smem, st>>>(mp);
         ARCHI_CHECK_LAUNCH();
         probed = true;
@@ -1498,8 +1595,10 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     tp.c.qt_count = qt_count;
     tp.c.ngroups = ngroups;
     tp.c.cap = cap;
-    tp.c.kprime = kprime;
+    tp.c.kprime = margin ? k : kprime;
     tp.thr_g = w.thr_g;
+    tp.qinfo = reinterpret_cast<const QInfo *>(w.qinfo);
+    tp.margin = margin;
     if (s->timing && !probed) ARCHI_CUDA(cudaEventRecord(s->ws.ev0, st));
     for (int ph = 0; ph < n_phases; ++ph) {
         cp.tile_begin = bounds[ph];
@@ -1538,22 +1637,24 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     sp.ngroups = ngroups;
     sp.cap = cap;
     sp.k = k;
-    sp.kprime = kprime;
+    sp.kprime = margin ? k : kprime;
+    sp.margin = margin;
     sp.out_scores = out_scores;
     sp.out_ids = reinterpret_cast<long long *>(out_ids);
     sp.id_offset = id_offset;
     sp.unverified = w.unverified;
     sp.n_unverified = w.unverified + nq_pad;
+    sp.unv_list = w.unv_list;
+    sp.max_sel = max_sel;
+    sp.sticky = w.sticky_dev;
     const size_t q_smem = (size_t)s->ld * sizeof(float);
-    ARCHI_CUDA(cudaFuncSetAttribute((const void *)tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_smem));
+    if ((rc = set_dyn_smem_once((const void *)tc_select_kernel, (int)q_smem)) != ARCHI_OK) return rc;
     tc_select_kernel<<<nq, SEL_THREADS, q_smem, st>>>(sp);
     ARCHI_CHECK_LAUNCH();
-
-    // ---- the proof's verdict (4 bytes + flags) ----
-    ARCHI_CUDA(cudaMemcpyAsync(n_unverified_host, w.unverified + nq_pad, 4, cudaMemcpyDeviceToHost, st));
-    ARCHI_CUDA(cudaStreamSynchronize(st));
-    if (*n_unverified_host > 0)
-        ARCHI_CUDA(cudaMemcpy(unverified_host, w.unverified, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    // No host round trip here: the caller enqueues the device-driven rescue of the listed queries
+    // (launch_rescue with qsel = w.unv_list, nsel = the counter) and reads the verdict when it next
+    // synchronises anyway.
+    *max_sel_out = max_sel;
     s->stats.grid = grid;
     s->stats.coarse_dtype = tf32 ? ARCHI_F32 : ARCHI_BF16;
     s->stats.coarse_launches = n_phases + (probed ? 1 : 0);
@@ -1562,9 +1663,12 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
 
 void free_tensor_workspace(TensorWorkspace &w)
 {
-    void *ptrs[] = {w.qstage, w.qinfo, w.thr_g, w.unverified, w.cand, w.cand_cnt, w.aux, w.max_norm2, w.shadow, w.chunkmax};
+    void *ptrs[] = {w.qstage, w.qinfo, w.thr_g, w.unverified, w.cand, w.cand_cnt, w.aux, w.max_norm2, w.shadow, w.chunkmax,
+                    w.unv_list, w.sticky_dev};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (w.h_verdict) cudaFreeHost(w.h_verdict);
+    if (w.verdict_ev) cudaEventDestroy(w.verdict_ev);
     w = TensorWorkspace();
 }
 

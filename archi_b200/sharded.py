@@ -139,6 +139,7 @@ class ShardedStore:
         self._local_rows = local_rows or (lambda: self.native.rows())
         self.id_offset = 0
         self.total_rows = 0
+        self._records = {}              # (nq, k, device) -> packed record buffer of _search_packed
         self._exchange = None           # PeerExchange, or False once found unavailable
         self.exchange_kind = "nccl"     # what search() uses between the ranks: "nccl" | "peer-memory"
 
@@ -195,7 +196,14 @@ class ShardedStore:
         nq = 1 if queries.dim() == 1 else int(queries.shape[0])
         n = nq * k
         rec = (n * 12 + 15) // 16 * 16      # the exchange kernel moves 16-byte words
-        mine = torch.empty(rec, dtype=torch.uint8, device=queries.device)
+        # this rank's record is scratch between the local search and the exchange of one call (stream-ordered):
+        # one buffer per shape, not one allocation per search
+        key = (nq, k, queries.device)
+        mine = self._records.get(key)
+        if mine is None:
+            if len(self._records) > 16:
+                self._records.clear()
+            mine = self._records[key] = torch.empty(rec, dtype=torch.uint8, device=queries.device)
         ids = mine[:n * 8].view(torch.int64).view(nq, k)
         scores = mine[n * 8:n * 12].view(torch.float32).view(nq, k)
         self._local_search(queries, k, self.id_offset, out=(scores, ids))

@@ -47,6 +47,7 @@ class NativeStore:
             raise ValueError("storage_dtype must be 'f32' or 'bf16'")
         self.dim, self.metric, self.storage_dtype, self.device = int(dim), metric, storage_dtype, int(device)
         self._L = N.lib()
+        self.last_hybrid_path = "none"
         if _handle is None:
             h = ctypes.c_void_p()
             N.check(self._L.archi_store_create(self.device, self.dim, N.METRICS[metric],
@@ -207,6 +208,52 @@ class NativeStore:
         else:
             N.check(self._L.archi_search(self._h, ctypes.c_void_p(qp), loc, nq, k, fm, int(include_deleted), int(path),
                                          ctypes.c_void_p(sp), ctypes.c_void_p(ip_), loc, int(id_offset), stream))
+        return scores, ids
+
+    def hybrid_search_terms(self, lexical, text_queries, queries, k: int, semantic_weight: float, bm25_weight: float,
+                            filter_mask=None, include_deleted: bool = False, id_offset: int = 0):
+        """hybrid_search over posting lists (archi_hybrid_search_terms): ``lexical`` is the collection's
+        LexicalIndex, ``text_queries`` one lexical query per embedding in ``queries`` (a string, or an array of
+        term keys).  numpy embeddings -> numpy outputs, torch CUDA embeddings -> torch CUDA outputs (nothing
+        synchronised).  Scores are the combined scores, best first.  ``last_hybrid_path`` says which path ran."""
+        k = int(k)
+        ranges = [lexical.posting_ranges(tq) for tq in text_queries]
+        counts = [r[0].size for r in ranges]
+        term_query = np.repeat(np.arange(len(ranges), dtype=np.int32), counts)
+        starts = np.concatenate([r[0] for r in ranges]) if ranges else np.empty(0, np.int64)
+        ends = np.concatenate([r[1] for r in ranges]) if ranges else np.empty(0, np.int64)
+        idf = np.concatenate([r[2] for r in ranges]) if ranges else np.empty(0, np.float32)
+        doc_ids, tfs, doc_len = lexical.device_arrays()
+        terms = N.Bm25Terms(int(term_query.size), term_query.ctypes.data, starts.ctypes.data, ends.ctypes.data, idf.ctypes.data,
+                            doc_ids.data_ptr(), tfs.data_ptr(), doc_len.data_ptr(), float(lexical.avgdl()),
+                            float(lexical.k1), float(lexical.b), float(lexical.sign))
+        fm = ctypes.c_void_p(filter_mask.data_ptr()) if filter_mask is not None else None
+        stream = ctypes.c_void_p(_current_stream_ptr(self.device))
+        if _is_torch_tensor(queries):
+            import torch
+            q = queries.contiguous().to(torch.float32)
+            if q.dim() == 1:
+                q = q[None, :]
+            nq = q.shape[0]
+            scores = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            qp, sp, ip_, loc = q.data_ptr(), scores.data_ptr(), ids.data_ptr(), N.DEVICE
+        else:
+            q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries, dtype=np.float32)))
+            nq = q.shape[0]
+            scores = np.empty((nq, k), dtype=np.float32)
+            ids = np.empty((nq, k), dtype=np.int64)
+            qp, sp, ip_, loc = q.ctypes.data, scores.ctypes.data, ids.ctypes.data, N.HOST
+        if nq != len(ranges):
+            raise ValueError("one lexical query per embedding is required")
+        if q.shape[1] != self.dim:
+            raise ValueError(f"query dimension {q.shape[1]} != store dimension {self.dim}")
+        path = ctypes.c_int(0)
+        N.check(self._L.archi_hybrid_search_terms(self._h, ctypes.c_void_p(qp), loc, nq, k, float(semantic_weight),
+                                                  float(bm25_weight), ctypes.byref(terms), fm, int(include_deleted),
+                                                  ctypes.c_void_p(sp), ctypes.c_void_p(ip_), loc, int(id_offset), stream,
+                                                  ctypes.byref(path)))
+        self.last_hybrid_path = {1: "posting-lists", 2: "dense-vector"}.get(path.value, "none")
         return scores, ids
 
     def last_stats(self) -> N.SearchStats:

@@ -305,10 +305,9 @@ class B200VectorStore(_VectorStoreBase):
             results: List[Tuple[Document, float]] = []
             if coll.native is not None and k > 0:
                 mask = self._where_mask(metadata_filter, include_deleted)
-                bm25 = coll.lexical.score(query)
-                scores, ids = coll.native.search(np.asarray(query_embedding, dtype=np.float32), k, filter_mask=mask,
-                                                 bm25=bm25, semantic_weight=semantic_weight, bm25_weight=bm25_weight,
-                                                 hybrid=True)
+                # posting lists of the query terms go straight to the kernel: no per-row BM25 vector
+                scores, ids = coll.native.hybrid_search_terms(coll.lexical, [query], np.asarray(query_embedding, dtype=np.float32),
+                                                              k, semantic_weight, bm25_weight, filter_mask=mask)
                 results = self._rows_to_results(ids[0], scores[0])
         if not results:
             return self.similarity_search_with_score(query, k=k, **kwargs)

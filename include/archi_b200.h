@@ -14,11 +14,16 @@
  *   - plain pointers and sizes only.  `*_loc` arguments say where a buffer lives
  *     (ARCHI_HOST / ARCHI_DEVICE).  Device pointers must belong to the store's device.
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls whose
- *     inputs and outputs are all on the device only enqueue work; calls with a host output
- *     synchronise the stream before returning.
- *   - a store handle may be shared between threads; calls on one handle serialise on an internal
- *     mutex (the reference store is stateless per call and therefore re-entrant under Flask
- *     threads, postgres_vectorstore.py:94-103).
+ *     inputs and outputs are all on the device only ENQUEUE work -- no host synchronisation, no
+ *     device-to-host copy the host waits for -- so searches pipeline back to back and can be
+ *     captured in a CUDA graph once the workspaces are warm; calls with a host output synchronise
+ *     the stream once, before returning.
+ *   - a store handle may be shared between threads; the host side of calls on one handle
+ *     serialises on an internal mutex (held while work is enqueued, not while the GPU runs it),
+ *     and a call on another stream than the previous call on the handle first waits, on the
+ *     device, for that call's work: rows, tombstones and scratch are shared by the handle.  (The
+ *     reference store is stateless per call and therefore re-entrant under Flask threads,
+ *     postgres_vectorstore.py:94-103.)
  *   - row ids are dense row indices in insertion order (the reference uses a SERIAL column,
  *     src/cli/templates/init.sql:256-276); `id_offset` is added on output so row-sharded stores
  *     can return global ids.
@@ -32,7 +37,7 @@
 extern "C" {
 #endif
 
-#define ARCHI_ABI_VERSION 1
+#define ARCHI_ABI_VERSION 2
 
 /* distance metric: postgres_vectorstore.py:74-78 ("cosine" <=>, "l2" <->, "inner_product" <#>) */
 enum { ARCHI_COSINE = 0, ARCHI_L2 = 1, ARCHI_IP = 2 };
@@ -112,7 +117,11 @@ int archi_pool_normalize_append(archi_store_t *s, const void *hidden_dev, int hi
  * Outputs, best first per query: out_scores [nq, k] fp32 in the reference's score convention
  * (cosine: similarity; l2: distance; inner_product: NEGATIVE inner product), out_ids [nq, k]
  * int64 = row id + id_offset.  When fewer than k rows pass, the tail is id -1 / score NaN.
- * Ties on the score are broken by the lower row id. */
+ * Ties on the score are broken by the lower row id.
+ * Batches of >= 2 queries take the tensor-core path: a bf16 coarse pass nominates candidates, every
+ * returned row is re-scored exactly in fp32 and each query carries a proof that no rejected row can
+ * belong to its top-k; a query whose proof fails is re-scanned by the exact streaming kernel inside
+ * the same call, driven from the device (no host round trip). */
 int archi_search(archi_store_t *s, const float *queries, int queries_loc, int nq, int k,
                  const uint32_t *filter_mask_dev, int include_deleted, int path,
                  float *out_scores, int64_t *out_ids, int out_loc, int64_t id_offset,
@@ -127,6 +136,31 @@ int archi_hybrid_search(archi_store_t *s, const float *queries, int queries_loc,
                         const uint32_t *filter_mask_dev, int include_deleted,
                         float *out_scores, int64_t *out_ids, int out_loc, int64_t id_offset,
                         void *stream);
+
+/* The same statement without a per-row BM25 vector: the query terms' posting lists go in directly.
+ * For rows without a lexical match combined = w_sem * semantic, so (w_sem > 0, bm25 >= 0) the exact fused top-k is
+ * the top-k of (dense top-k over all rows  U  exact combined score of the rows matching a term): one ordinary
+ * search (tensor-core path for batches) plus work proportional to the postings of the query terms.  Queries whose
+ * terms match more than 1/8 of the rows (or sign < 0, w_sem <= 0) take the dense-vector scan of archi_hybrid_search.
+ * terms: (query, term) occurrences grouped by query -- term_query[j] ascending in [0, nq) --, each with its posting
+ * range [post_start[j], post_end[j]) into doc_ids_dev / tfs_dev and its idf (host arrays); doc_len_dev [rows].
+ * BM25(row) = sum_j idf[j] * tf*(k1+1) / (tf + k1*(1 - b + b*doc_len[row]/avgdl)) * sign, rows never touched are
+ * SQL NULL (COALESCE -> 0).  *out_path (may be NULL): 1 = posting-list path, 2 = dense-vector path. */
+typedef struct {
+    int n_terms;
+    const int32_t *term_query;
+    const int64_t *post_start;
+    const int64_t *post_end;
+    const float *idf;
+    const int32_t *doc_ids_dev;
+    const int32_t *tfs_dev;
+    const float *doc_len_dev;
+    float avgdl, k1, b, sign;
+} archi_bm25_terms_t;
+int archi_hybrid_search_terms(archi_store_t *s, const float *queries, int queries_loc, int nq, int k,
+                              float w_sem, float w_bm25, const archi_bm25_terms_t *terms,
+                              const uint32_t *filter_mask_dev, int include_deleted, float *out_scores,
+                              int64_t *out_ids, int out_loc, int64_t id_offset, void *stream, int *out_path);
 
 /* BM25 over device posting lists (replaces pg_textsearch's `chunk_text <@> to_bm25query(...)`,
  * postgres_vectorstore.py:433).  For each query term t (n_terms of them) with postings
@@ -188,13 +222,18 @@ typedef struct {
     int path;              /* ARCHI_PATH_STREAM | ARCHI_PATH_TENSOR */
     int passes;            /* corpus passes */
     int grid;              /* CTAs of the dominant kernel */
-    int unverified_queries;/* tensor path: queries re-run on the exact path */
+    int unverified_queries;/* tensor path: queries whose exactness proof failed and that were re-scanned exactly */
     double last_kernel_ms; /* device time of the dominant kernel(s) (CUDA events), if requested: the scan
                               kernel of one pass, or the tensor path's coarse launches + threshold kernels */
     int coarse_dtype;      /* tensor path: element type the coarse pass read (ARCHI_BF16: bf16 rows or the
                               bf16 shadow of fp32 rows; ARCHI_F32: fp32 rows as tf32) */
     int coarse_launches;   /* tensor path: coarse-kernel launches per pass (warm-up phases + main) */
+    int unproven_queries;  /* running total since the store was created: queries returned as id -1 / score NaN
+                              because more proofs failed in one launch than the device-side rescue list holds
+                              (256).  Only possible for batches > 256 with DEVICE outputs; with host outputs
+                              such queries are re-scanned before the call returns. */
 } archi_search_stats_t;
+/* Synchronises with the last search on the handle (the proof verdicts travel asynchronously). */
 int archi_store_last_stats(archi_store_t *s, archi_search_stats_t *out);
 /* When enabled, archi_search brackets its dominant kernel with CUDA events on the caller's
  * stream and synchronises to fill last_kernel_ms (bench.py's roofline leg). */

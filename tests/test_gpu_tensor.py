@@ -125,6 +125,70 @@ def test_tensor_path_duplicates_and_failed_proofs_fall_back_to_exact():
     s.close()
 
 
+def test_failed_proofs_are_rescued_on_the_device_without_a_host_round_trip():
+    """Device outputs: nothing synchronises inside archi_search, the queries whose proof failed are re-scanned
+    by launches driven from a device-side list.  Every query of a batch <= 256 can be rescued."""
+    import torch
+    rng = np.random.default_rng(5)
+    center = unit_rows(rng, 1, 96)
+    corpus = (center + 1e-5 * rng.standard_normal((6000, 96))).astype(np.float32)
+    s = make_store(corpus, "inner_product")
+    qq = unit_rows(rng, 200, 96)
+    sc, ids = s.search(torch.from_numpy(qq).cuda(), 10, path=TENSOR)
+    st = s.last_stats()                                        # synchronises with the search
+    assert st.unverified_queries > 100 and st.unproven_queries == 0
+    check_against_truth("inner_product", corpus, qq, 10, sc.cpu().numpy(), ids.cpu().numpy(), REL_F32)
+    s.close()
+
+
+def test_more_failed_proofs_than_the_rescue_list_holds():
+    """Batches > 256 whose proofs (almost) all fail: with host outputs the call re-scans every flagged query
+    before it returns (still exact); with device outputs the queries beyond the 256 rescued ones come back as
+    id -1 / score NaN -- never as an unproven row -- and are counted in unproven_queries."""
+    import torch
+    rng = np.random.default_rng(6)
+    center = unit_rows(rng, 1, 64)
+    corpus = (center + 1e-5 * rng.standard_normal((5000, 64))).astype(np.float32)
+    qq = unit_rows(rng, 300, 64)
+    s = make_store(corpus, "inner_product")
+    scores, ids = s.search(qq, 10, path=TENSOR)                # host buffers
+    assert s.last_stats().unverified_queries > 256
+    check_against_truth("inner_product", corpus, qq, 10, scores, ids, REL_F32)
+    sc_d, id_d = s.search(torch.from_numpy(qq).cuda(), 10, path=TENSOR)
+    st = s.last_stats()
+    sc_d, id_d = sc_d.cpu().numpy(), id_d.cpu().numpy()
+    poisoned = (id_d[:, 0] == -1)
+    assert st.unproven_queries == poisoned.sum() == st.unverified_queries - 256
+    assert (id_d[poisoned] == -1).all() and np.isnan(sc_d[poisoned]).all()
+    good = ~poisoned
+    assert np.array_equal(id_d[good], ids[good]) and np.array_equal(sc_d[good], scores[good])
+    s.close()
+
+
+def test_searches_on_different_streams_are_ordered_on_the_device():
+    """The handle's scratch is shared: a search on another stream waits for the previous call's work."""
+    import torch
+    rng = np.random.default_rng(7)
+    corpus = unit_rows(rng, 50000, 128)
+    s = make_store(corpus)
+    qa, qb = unit_rows(rng, 64, 128), unit_rows(rng, 64, 128)
+    want_a, want_b = s.search(qa, 10), s.search(qb, 10)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    da, db = torch.from_numpy(qa).cuda(), torch.from_numpy(qb).cuda()
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(6):
+        with torch.cuda.stream(s1):
+            outs.append(("a", s.search(da, 10)))
+        with torch.cuda.stream(s2):
+            outs.append(("b", s.search(db, 10)))
+    torch.cuda.synchronize()
+    for which, (sc, ids) in outs:
+        want = want_a if which == "a" else want_b
+        assert np.array_equal(ids.cpu().numpy(), want[1]) and np.array_equal(sc.cpu().numpy(), want[0])
+    s.close()
+
+
 def test_auto_path_switches_by_batch_size():
     rng = np.random.default_rng(8)
     corpus = unit_rows(rng, 9000, 64)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in archi_b200.h but not exported"
     assert sorted(N.EXPORTS) == declared
-    assert L.archi_abi_version() == 1
+    assert L.archi_abi_version() == 2
 
 
 def test_no_silent_cpu_fallback_without_gpu():

@@ -90,6 +90,13 @@ class _StandInNative:
     def close(self):
         pass
 
+    def hybrid_search_terms(self, lexical, text_queries, queries, k, semantic_weight, bm25_weight, filter_mask=None,
+                            include_deleted=False, id_offset=0):
+        from test_lexical_host import bm25_from_csr
+        bm = np.stack([np.nan_to_num(bm25_from_csr(lexical, tq), nan=0.0) for tq in text_queries])
+        return self.search(queries, k, filter_mask=filter_mask, include_deleted=include_deleted, bm25=bm,
+                           semantic_weight=semantic_weight, bm25_weight=bm25_weight, hybrid=True)
+
     def search(self, queries, k, filter_mask=None, include_deleted=False, bm25=None, semantic_weight=1.0,
                bm25_weight=0.0, hybrid=False, **_):
         q = np.atleast_2d(np.asarray(queries, dtype=np.float32))
