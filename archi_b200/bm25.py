@@ -197,6 +197,35 @@ class LexicalIndex:
     def reset(self) -> None:
         self.__init__(self.device, self.k1, self.b, self.sign, self.tokenize, self.table)
 
+    def save(self, path: str) -> None:
+        """The index state (per-chunk (term key, tf) pairs, chunk lengths, tombstones) as one .npz; the device
+        posting lists are rebuilt from it on the first search after ``load``."""
+        if self._batches:
+            keys = np.concatenate([b[0] for b in self._batches])
+            tfs = np.concatenate([b[1] for b in self._batches])
+            counts = np.concatenate([b[2] for b in self._batches])
+            lens = np.concatenate([b[3] for b in self._batches])
+        else:
+            keys, tfs = np.empty(0, np.uint64), np.empty(0, np.int32)
+            counts, lens = np.empty(0, np.int64), np.empty(0, np.int32)
+        vocab = np.asarray(sorted(self._vocab.items(), key=lambda kv: kv[1]), dtype=object) if self._vocab else np.empty((0, 2), dtype=object)
+        np.savez_compressed(path, keys=keys, tfs=tfs, counts=counts, lens=lens,
+                            deleted=np.asarray(sorted(self._deleted), dtype=np.int64),
+                            params=np.asarray([self.k1, self.b, self.sign, float(self._fast)]),
+                            vocab_tokens=np.asarray([t for t, _ in vocab], dtype=str) if len(vocab) else np.empty(0, dtype=str))
+
+    def load(self, path: str) -> None:
+        z = np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False)
+        self._batches = [(z["keys"], z["tfs"], z["counts"], z["lens"])] if z["counts"].size else []
+        self._n_docs = int(z["counts"].size)
+        self._deleted = set(int(r) for r in z["deleted"])
+        self.k1, self.b, self.sign = (float(v) for v in z["params"][:3])
+        if bool(z["params"][3]) != self._fast:
+            raise RuntimeError("the snapshot's lexical index was built with a different tokeniser path "
+                               "(libarchi_text.so present / absent): re-tokenise with add_texts instead")
+        self._vocab = {str(t): i for i, t in enumerate(z["vocab_tokens"])}
+        self._dirty = True
+
     def detach(self) -> None:
         """Leave the table statistics (the collection is dropped)."""
         if self in self.table.members:

@@ -230,6 +230,7 @@ static int search_core(archi_store *s, const float *q_dev, int nq, int k, const 
                     rc = rescan_flagged(s, a, q_dev + (size_t)q0 * s->dim, nb, k, o_scores + (size_t)q0 * k,
                                         o_ids + (size_t)q0 * k, id_offset, st);
                     if (rc != ARCHI_OK) return rc;
+                    tw.sticky_fixed += tw.h_verdict[slot] - max_sel;     // those queries were answered after all
                 }
             }
         }
@@ -363,6 +364,7 @@ static int search_impl(archi_store *s, const float *queries, int queries_loc, in
             a.bias_stride = s->rows;
             if ((rc = rescan_flagged(s, a, io.q_dev, nq, k, io.o_scores, io.o_ids, id_offset, st)) != ARCHI_OK) return rc;
             if ((rc = copy_outputs_to_host(io, nq, k, out_scores, out_ids, st)) != ARCHI_OK) return rc;
+            tw.sticky_fixed += tw.h_verdict[0] - tw.verdict_max_sel[0];  // those queries were answered after all
         }
     }
     return mark_done(s, st);
@@ -926,6 +928,13 @@ int archi_bm25_accumulate(const int64_t *post_start_host, const int64_t *post_en
     ARCHI_REQUIRE(n_terms == 0 || (post_start_host && post_end_host && idf_host && out_dev && doc_len_dev),
                   "bm25_accumulate: null argument");
     ARCHI_REQUIRE(avgdl > 0.f, "bm25_accumulate: avgdl must be positive");
+    if (n_terms == 0) return ARCHI_OK;
+    // launch on the device that owns the output vector, whatever the caller's current device is
+    cudaPointerAttributes attr;
+    ARCHI_CUDA(cudaPointerGetAttributes(&attr, out_dev));
+    ARCHI_REQUIRE(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged,
+                  "bm25_accumulate: out_dev is not device memory");
+    ARCHI_DEVICE_GUARD(attr.device);
     for (int t = 0; t < n_terms; ++t) {
         const int64_t b0 = post_start_host[t], b1 = post_end_host[t];
         ARCHI_REQUIRE(b0 >= 0 && b1 >= b0, "bm25_accumulate: bad posting range [%lld, %lld)", (long long)b0, (long long)b1);
@@ -976,7 +985,7 @@ int archi_store_last_stats(archi_store_t *s, archi_search_stats_t *out)
         s->stats.unverified_queries = total;
         int sticky = 0;
         ARCHI_CUDA(cudaMemcpy(&sticky, tw.sticky_dev, sizeof(int), cudaMemcpyDeviceToHost));
-        s->stats.unproven_queries = sticky;
+        s->stats.unproven_queries = sticky - tw.sticky_fixed;
         tw.verdict_pending = false;
     }
     *out = s->stats;

@@ -89,6 +89,7 @@ struct TensorWorkspace {
     int64_t shadow_rows = 0;     // rows [0, shadow_rows) are converted
     int64_t shadow_reset_epoch = -1;
     int64_t maxnorm_epoch = -1;
+    bool maxnorm_all_rows = false;   // the cached norm bounds include tombstoned rows (include_deleted searches)
     int64_t aux_epoch = -1;
     bool aux_alive = false, aux_had_filter = false;
     // queries whose exactness proof failed: device list [unv_cap] filled by tc_select_kernel, re-scanned by
@@ -100,7 +101,8 @@ struct TensorWorkspace {
     int verdict_launches = 0;
     cudaEvent_t verdict_ev = nullptr;
     bool verdict_pending = false;
-    int *sticky_dev = nullptr;   // device [1]: queries ever returned as id -1 / NaN because the rescue list was full
+    int *sticky_dev = nullptr;   // device [1]: queries ever written as id -1 / NaN because the rescue list was full
+    int sticky_fixed = 0;        // ... of which the host re-scanned before returning (host outputs)
     // TMA descriptors are rebuilt only when what they describe changes
     unsigned char tmap_q[128] __attribute__((aligned(64)));
     unsigned char tmap_c[128] __attribute__((aligned(64)));

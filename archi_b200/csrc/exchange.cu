@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(kExchThreads) exchange_merge_kernel(const Exch
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_last;
+    __shared__ int s_bad;      // a wait gave up in this call or in an earlier one: the gather buffer cannot be trusted
+    if (tid == 0) s_bad = *reinterpret_cast<volatile int *>(p.status);
 
     // ---- 1. push my record into slot [parity][rank] of every peer (myself included) ----
     const size_t vecs = p.rec_bytes / 16;
@@ -89,13 +91,24 @@ __global__ void __launch_bounds__(kExchThreads) exchange_merge_kernel(const Exch
         const unsigned long long t0 = global_timer_ns();
         while ((int)(ld_acquire_sys(flag) - p.epoch) < 0) {
             if (global_timer_ns() - t0 > p.timeout_ns) {
-                atomicExch(p.status, 1);
+                *reinterpret_cast<volatile int *>(p.status) = 1;      // host-mapped and sticky: the next call fails on the host
+                __threadfence_system();
+                s_bad = 1;
                 break;
             }
             __nanosleep(100);
         }
     }
     __syncthreads();
+    if (s_bad) {
+        // never merge a stale or half-written slot into plausible results: poison this call's outputs
+        const size_t n_out = (size_t)p.nq * p.k;
+        for (size_t i = (size_t)blockIdx.x * kExchThreads + tid; i < n_out; i += (size_t)gridDim.x * kExchThreads) {
+            p.out_scores[i] = __int_as_float(0x7fc00000);
+            p.out_ids[i] = -1;
+        }
+        return;
+    }
 
     // ---- 4. merge the world lists of each query from the local gather buffer ----
     const unsigned char *mine = p.peer_base[p.rank] + (size_t)p.parity * p.world * p.slot_bytes;
@@ -117,6 +130,8 @@ struct archi_exchange {
     size_t slot_bytes = 0, flags_off = 0, total_bytes = 0;
     unsigned char *local = nullptr;               // cudaMalloc'ed: [2][world][slot] | flags [world] | counter | status
     unsigned char *peer[archi::kExchMaxWorld] = {};
+    int *h_status = nullptr;                      // pinned + mapped: 1 once any wait timed out (sticky)
+    int *d_status = nullptr;                      // the device alias the kernel writes
     bool connected = false;
     uint32_t epoch = 0;
     std::mutex mu;
@@ -163,9 +178,15 @@ int archi_exchange_create(int device, int rank, int world, int64_t max_record_by
     x->total_bytes = x->flags_off + (size_t)world * 4 + 64;   // + counter, status (local use only)
     cudaError_t e = cudaMalloc(&x->local, x->total_bytes);
     if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->total_bytes);
+    if (e == cudaSuccess) e = cudaHostAlloc(&x->h_status, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *x->h_status = 0;
+        e = cudaHostGetDevicePointer(&x->d_status, x->h_status, 0);
+    }
     if (e != cudaSuccess) {
         archi::set_error("exchange_create: allocating %zu bytes failed: %s", x->total_bytes, cudaGetErrorString(e));
         if (x->local) cudaFree(x->local);
+        if (x->h_status) cudaFreeHost(x->h_status);
         delete x;
         return ARCHI_ECUDA;
     }
@@ -224,6 +245,11 @@ int archi_exchange_merge_topk(archi_exchange_t *x, const void *record_dev, int n
     ARCHI_REQUIRE(rec <= x->slot_bytes, "exchange_merge_topk: record of %zu bytes exceeds the slot (%zu bytes)", rec,
                   x->slot_bytes);
     ARCHI_REQUIRE(((uintptr_t)record_dev & 15) == 0, "exchange_merge_topk: record must be 16-byte aligned");
+    if (*reinterpret_cast<volatile int *>(x->h_status) != 0) {
+        archi::set_error("exchange_merge_topk: an earlier exchange timed out waiting for a rank; the results of that call "
+                         "were invalidated (id -1 / NaN) and the ranks' epochs may be skewed -- rebuild the exchange");
+        return ARCHI_ECUDA;
+    }
     EXCH_DEVICE(x->device);
     archi::ExchangeParams p;
     for (int r = 0; r < archi::kExchMaxWorld; ++r) p.peer_base[r] = r < x->world ? x->peer[r] : nullptr;
@@ -242,7 +268,7 @@ int archi_exchange_merge_topk(archi_exchange_t *x, const void *record_dev, int n
     p.out_scores = out_scores_dev;
     p.out_ids = (long long *)out_ids_dev;
     p.counter = reinterpret_cast<unsigned int *>(x->local + x->flags_off + (size_t)x->world * 4);
-    p.status = reinterpret_cast<int *>(x->local + x->flags_off + (size_t)x->world * 4 + 16);
+    p.status = x->d_status;
     p.timeout_ns = 5ull * 1000 * 1000 * 1000;
     int grid = (nq + archi::kExchThreads / 32 - 1) / (archi::kExchThreads / 32);
     if (grid < 8) grid = 8;
@@ -257,8 +283,7 @@ int archi_exchange_status(archi_exchange_t *x, int *timed_out)
     ARCHI_REQUIRE(x && timed_out, "exchange_status: null argument");
     EXCH_DEVICE(x->device);
     ARCHI_CUDA(cudaDeviceSynchronize());
-    ARCHI_CUDA(cudaMemcpy(timed_out, x->local + x->flags_off + (size_t)x->world * 4 + 16, sizeof(int),
-                          cudaMemcpyDeviceToHost));
+    *timed_out = *reinterpret_cast<volatile int *>(x->h_status);
     return ARCHI_OK;
 }
 
@@ -271,6 +296,7 @@ int archi_exchange_destroy(archi_exchange_t *x)
         for (int r = 0; r < x->world; ++r)
             if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
         if (x->local) cudaFree(x->local);
+        if (x->h_status) cudaFreeHost(x->h_status);
     }
     delete x;
     return ARCHI_OK;

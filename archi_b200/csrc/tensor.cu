@@ -1409,10 +1409,11 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
 
     // ---- cached per-store data: max |row|^2 and the (a, b) constants ----
     const uint32_t *alive = include_deleted ? nullptr : s->alive;
-    if (w.maxnorm_epoch != s->epoch) {
+    if (w.maxnorm_epoch != s->epoch || w.maxnorm_all_rows != (include_deleted != 0)) {
         const uint32_t init[2] = {0u, 0x7f800000u};   // max = 0, min = +inf
         ARCHI_CUDA(cudaMemcpyAsync(w.max_norm2, init, 8, cudaMemcpyHostToDevice, st));
-        tc_maxnorm_kernel<<<s->sm_count * 2, 256, 0, st>>>(s->norm2, s->alive, s->rows, w.max_norm2);
+        // the bounds must cover every row the scan can return: tombstoned rows too when include_deleted is set
+        tc_maxnorm_kernel<<<s->sm_count * 2, 256, 0, st>>>(s->norm2, alive, s->rows, w.max_norm2);
         ARCHI_CHECK_LAUNCH();
         float h[2];
         ARCHI_CUDA(cudaMemcpyAsync(h, w.max_norm2, 8, cudaMemcpyDeviceToHost, st));
@@ -1420,6 +1421,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         w.h_max_norm2 = h[0];
         w.h_min_norm2 = h[1];
         w.maxnorm_epoch = s->epoch;
+        w.maxnorm_all_rows = include_deleted != 0;
     }
     // Raw-key epilogue (no per-column constants): inner product always; cosine when the rows the
     // coarse pass reads are unit length -- exactly (normalised bf16 shadow of an fp32 store) or within

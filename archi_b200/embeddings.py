@@ -131,3 +131,9 @@ class B200Embeddings:
 
     def embed_query(self, text: str) -> List[float]:
         return self.embed_documents_device([text])[0].cpu().tolist()
+
+    def embed_query_device(self, text: str):
+        """[1, H] fp32 CUDA tensor: the query embedding straight from the pool+normalise kernel.  B200VectorStore
+        passes it to the search kernels as a device pointer -- the reference turns the vector into decimal text
+        for the SQL statement (postgres_vectorstore.py:313,391)."""
+        return self.embed_documents_device([text])[:1]

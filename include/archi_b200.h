@@ -204,8 +204,10 @@ int archi_merge_topk_strided(int device, const float *scores_dev, const int64_t 
  *                                on the device; it is pushed into every peer's buffer, the kernel waits
  *                                (bounded, 5 s) for all world records of this call and writes the merged
  *                                [nq,k] lists.  larger_is_better as in archi_merge_topk.
- *   archi_exchange_status        synchronises the device; *timed_out = 1 if any call gave up waiting
- *                                (its outputs are then invalid).
+ *                                A call whose wait times out writes id -1 / score NaN into ALL its outputs (never a
+ *                                merge of stale slots) and latches a host-visible status: every later
+ *                                archi_exchange_merge_topk on the handle returns an error without launching.
+ *   archi_exchange_status        synchronises the device; *timed_out = 1 if any call gave up waiting.
  * archi_exchange_destroy must be preceded by a barrier across the ranks. */
 #define ARCHI_EXCHANGE_HANDLE_BYTES 64
 typedef struct archi_exchange archi_exchange_t;

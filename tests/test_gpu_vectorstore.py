@@ -100,19 +100,27 @@ class TableEmbeddings:
         return self._vec(text).tolist()
 
 
-@pytest.fixture
-def fresh_store():
+@pytest.fixture(params=[1, 2, 8], ids=["1gpu", "2gpus", "8gpus"])
+def fresh_store(request):
+    """The same suite runs on a single-GPU collection and on collections row-sharded over 2 and 8 GPUs of the
+    box (``devices=``): the reference-facing behaviour must not depend on where the rows live."""
+    import torch
     from archi_b200 import B200VectorStore
+    n_dev = request.param
+    if torch.cuda.device_count() < n_dev:
+        pytest.skip(f"needs {n_dev} GPUs")
+    devices = list(range(n_dev)) if n_dev > 1 else None
     names = []
 
     def make(name, **kw):
-        B200VectorStore.drop_collection(name)
+        B200VectorStore.drop_collection(name, devices=devices)
         names.append(name)
         return B200VectorStore(pg_config={}, embedding_function=kw.pop("emb", TableEmbeddings()),
-                               collection_name=name, **kw)
+                               collection_name=name, devices=devices, **kw)
+    make.devices = devices
     yield make
     for n in names:
-        B200VectorStore.drop_collection(n)
+        B200VectorStore.drop_collection(n, devices=devices)
 
 
 def test_add_and_search_conventions(fresh_store):
@@ -201,10 +209,11 @@ def test_store_objects_share_the_collection(fresh_store):
     emb = TableEmbeddings(32)
     a = fresh_store("t_shared", emb=emb)
     a.add_texts(["alpha", "beta"])
-    b = B200VectorStore(pg_config={}, embedding_function=emb, collection_name="t_shared")   # per-request construction
+    b = B200VectorStore(pg_config={}, embedding_function=emb, collection_name="t_shared",
+                        devices=fresh_store.devices)                                          # per-request construction
     assert b.count() == 2 and b.similarity_search("beta", k=1)[0].page_content == "beta"
     with pytest.raises(ValueError, match="metric is fixed"):
-        B200VectorStore(None, emb, "t_shared", "l2")
+        B200VectorStore(None, emb, "t_shared", "l2", devices=fresh_store.devices)
 
 
 def test_hybrid_search_matches_oracle(fresh_store):
@@ -257,6 +266,60 @@ def test_b200_embeddings_end_to_end(fresh_store):
     vs = fresh_store("t_e2e", emb=emb)
     vs.add_texts(texts)                                              # goes through pool_normalize_append
     assert vs.count() == 4
-    assert np.allclose(vs.native.read_rows(0, 4), vecs, rtol=1e-5, atol=2e-6)
+    stored = np.concatenate([sh.native.read_rows(0, len(sh.l2g)) for sh in vs._coll.shards if sh.l2g])
+    order = np.concatenate([sh.l2g for sh in vs._coll.shards if sh.l2g])
+    assert np.allclose(stored[np.argsort(order)], vecs, rtol=1e-5, atol=2e-6)
     top = vs.similarity_search_with_score(texts[1], k=1)[0]
     assert top[0].page_content == texts[1] and top[1] == pytest.approx(1.0, abs=1e-4)
+
+
+def test_collection_snapshot_and_pgvector_import(fresh_store, tmp_path):
+    """Restart story: save -> drop -> load gives the same answers (dense, filtered, hybrid, soft-deleted
+    documents, tombstones), and a collection rebuilt from the reference's wire format (`embedding::text`) too."""
+    from archi_b200 import B200VectorStore
+    emb = TableEmbeddings(64)
+    vs = fresh_store("t_snap", emb=emb)
+    texts = [f"{w} chunk {i} about {'muon' if i % 3 == 0 else 'jets'} triggers" for i, w in enumerate(["alpha", "beta", "gamma", "delta"] * 10)]
+    metas = [{"filename": f"f{i % 4}.md", "i": i} for i in range(40)]
+    vs.add_texts(texts[:20], metas[:20], ids=[f"c{i}" for i in range(20)], document_id=1)
+    vs.add_texts(texts[20:], metas[20:], ids=[f"c{i}" for i in range(20, 40)], document_id=2)
+    vs.register_document(1, resource_hash="h1", display_name="One", source_type="local", url="u1")
+    vs.register_document(2, resource_hash="h2", display_name="Two", source_type="web", url=None, is_deleted=True)
+    vs.delete(ids=["c3", "c4"])
+
+    def answers(store):
+        out = [store.similarity_search_with_score("alpha chunk 8 about jets triggers", k=6),
+               store.similarity_search_with_score("beta chunk 9", k=5, filter={"filename": "f1.md"}),
+               store.similarity_search_with_score("gamma", k=50, include_deleted=True),
+               store.hybrid_search("muon triggers", k=5, semantic_weight=0.4, bm25_weight=0.6)]
+        return [[(d.page_content, sorted(d.metadata.items(), key=str), round(float(s), 6)) for d, s in r] for r in out], store.count()
+
+    want = answers(vs)
+    snap = str(tmp_path / "snap")
+    vs.save(snap)
+    devices = fresh_store.devices
+    B200VectorStore.drop_collection("t_snap", devices=devices)
+    back = B200VectorStore.load(snap, emb, pg_config={}, devices=devices)
+    assert answers(back) == want
+    back.add_texts(["a brand new chunk"], [{"filename": "new.md"}], ids=["n0"])            # the restored store keeps working
+    assert back.similarity_search("a brand new chunk", k=1)[0].page_content == "a brand new chunk"
+    B200VectorStore.drop_collection("t_snap", devices=devices)
+
+    # the reference's table as it would be read back: embedding::text, metadata jsonb
+    import json
+    rows = []
+    for i, t in enumerate(texts):
+        if i in (3, 4):
+            continue                                                         # DELETEd rows are not in the table
+        v = emb._vec(t)
+        md = dict(metas[i], collection="t_import", chunk_id=f"c{i}")
+        rows.append((1 if i < 20 else 2, i % 20, t, "[" + ",".join(str(x) for x in v.tolist()) + "]", json.dumps(md)))
+    rows.append((9, 0, "other collection row", "[" + ",".join(["0.5"] * 64) + "]", {"collection": "somewhere_else"}))
+    imp = fresh_store("t_import", emb=emb)
+    assert imp.import_pgvector_rows(rows) == 38
+    imp.register_document(1, resource_hash="h1", display_name="One", source_type="local", url="u1")
+    imp.register_document(2, resource_hash="h2", display_name="Two", source_type="web", url=None, is_deleted=True)
+    got = answers(imp)
+    strip = lambda res: [[(t, [kv for kv in md if kv[0] != "collection"], s) for t, md, s in r] for r in res]  # noqa: E731
+    assert strip(got[0]) == strip(want[0]) and got[1] == want[1]
+    assert imp.delete(ids=["c7"]) and imp.count() == 37

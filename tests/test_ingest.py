@@ -74,8 +74,9 @@ def make_store(name, ef, monkeypatch):
     store = B200VectorStore({}, ef, collection_name=name, bm25_index=False)
     coll = store._coll
     fake = FakeNative(ef.dim)
-    monkeypatch.setattr(coll, "ensure_native", lambda dim: fake)
-    coll.native = fake
+    monkeypatch.setattr(coll, "ensure_native", lambda dim, shard=0: fake)
+    coll.shards[0].native = fake
+    coll.dim = ef.dim
     return store, fake
 
 
