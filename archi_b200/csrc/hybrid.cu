@@ -14,7 +14,7 @@
 //   3. hyb_fix_dense_kernel turns the dense scores into combined scores and drops dense rows that are in S_q;
 //   4. hyb_collect_kernel   walks the postings again: the first visitor of a row takes its BM25 sum (atomicExch
 //                           back to zero: the accumulator is clean again) and appends the row to the query's list;
-//   5. hyb_score_kernel     one warp per listed row: coalesced row load, exact fp32 dot, combined score,
+//   5. hyb_score_kernel     a warp per four listed rows: coalesced row loads, exact fp32 dot, combined score,
 //                           warp-register top-k, block merge -> partial lists;
 //   6. hyb_merge_kernel     dense list + partial lists -> the k best (combined desc, id asc).
 // Work per query is O(postings of its terms) + one dense search instead of O(rows) extra traffic and a memset.
@@ -29,7 +29,7 @@ namespace archi {
 
 constexpr int kHybMaxPairs = kHybMaxPairsHost;    // (query, term) pairs per round (kernel-parameter space)
 constexpr int kHybMaxSlots = kHybMaxSlotsHost;    // queries per round (accumulator planes)
-constexpr int kHybCps = 8;          // CTAs scoring the candidates of one query
+constexpr int kHybCpsMax = 296;     // most CTAs scoring the candidates of one query (cps is chosen per round)
 constexpr float kFix = 4294967296.0f;           // 2^32: BM25 contributions are accumulated in 32.32 fixed point
 constexpr float kUnfix = 2.3283064365386963e-10f;
 
@@ -132,8 +132,9 @@ struct HybScore {
     const int *cand_cnt;
     const int *cand_doc;
     const float *cand_bm;
-    float *part_key;             // [n_slots][kHybCps][k]
+    float *part_key;             // [n_slots][cps][k]
     int *part_id;
+    int cps;                     // CTAs per query slot
 };
 
 // Merge `nlists` sorted lists of 32*M entries staged in shared memory into `res` (same walk as scan.cu's block merge).
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const 
     extern __shared__ __align__(16) unsigned char hsmem[];
     float *sq = reinterpret_cast<float *>(hsmem);            // [ld] the slot's query, zero padded
     __shared__ float s_qrn;
-    const int slot = blockIdx.x / kHybCps, cta = blockIdx.x % kHybCps;
+    const int slot = blockIdx.x / p.cps, cta = blockIdx.x % p.cps;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int WARPS = 8;
     for (int e = tid; e < p.ld; e += 256) sq[e] = e < p.dim ? p.queries[(size_t)slot * p.dim + e] : 0.f;
@@ -188,53 +189,75 @@ __global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const 
     const size_t row_bytes = (size_t)p.ld * (p.dtype == ARCHI_BF16 ? 2 : 4);
     WarpTopK<M> list;
     list.init();
-    for (int i = cta * WARPS + warp; i < n; i += kHybCps * WARPS) {
-        const int doc = docs[i];
-        bool ok = true;
-        if (p.alive) ok = ok && ((p.alive[doc >> 5] >> (doc & 31)) & 1u);
-        if (p.filter) ok = ok && ((p.filter[doc >> 5] >> (doc & 31)) & 1u);
-        if (!ok) continue;                                   // warp-uniform
-        const uint4 *rp = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(p.corpus) + (size_t)doc * row_bytes);
-        float acc = 0.f;
-        for (int v = lane; v < nvec; v += 32) {
-            const uint4 d = __ldg(rp + v);
-            const float *qq = sq + v * vec;
-            float x[8];
-            if (p.dtype == ARCHI_BF16) {
-                x[0] = __uint_as_float(d.x << 16); x[1] = __uint_as_float(d.x & 0xffff0000u);
-                x[2] = __uint_as_float(d.y << 16); x[3] = __uint_as_float(d.y & 0xffff0000u);
-                x[4] = __uint_as_float(d.z << 16); x[5] = __uint_as_float(d.z & 0xffff0000u);
-                x[6] = __uint_as_float(d.w << 16); x[7] = __uint_as_float(d.w & 0xffff0000u);
-            } else {
-                x[0] = __uint_as_float(d.x); x[1] = __uint_as_float(d.y);
-                x[2] = __uint_as_float(d.z); x[3] = __uint_as_float(d.w);
-                x[4] = x[5] = x[6] = x[7] = 0.f;
-            }
+    // a warp takes four listed rows at a time and keeps the loads of all four in flight (random 16-byte-vector
+    // gathers are latency bound: one row per warp leaves the memory system idle)
+    constexpr int RW = 4;
+    for (int i0 = (cta * WARPS + warp) * RW; i0 < n; i0 += p.cps * WARPS * RW) {
+        int doc[RW];
+        bool ok[RW];
+        const uint4 *rp[RW];
+        float acc[RW];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (e < vec) {
-                    if (p.metric == ARCHI_L2) {
-                        const float t = x[e] - qq[e];
-                        acc = fmaf(t, t, acc);
-                    } else {
-                        acc = fmaf(x[e], qq[e], acc);
+        for (int j = 0; j < RW; ++j) {
+            const int i = i0 + j;
+            doc[j] = i < n ? docs[i] : 0;
+            ok[j] = i < n;
+            if (ok[j] && p.alive) ok[j] = (p.alive[doc[j] >> 5] >> (doc[j] & 31)) & 1u;
+            if (ok[j] && p.filter) ok[j] = (p.filter[doc[j] >> 5] >> (doc[j] & 31)) & 1u;
+            rp[j] = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(p.corpus) + (size_t)doc[j] * row_bytes);
+            acc[j] = 0.f;
+        }
+        for (int v = lane; v < nvec; v += 32) {
+            uint4 d[RW];
+#pragma unroll
+            for (int j = 0; j < RW; ++j) d[j] = ok[j] ? __ldg(rp[j] + v) : make_uint4(0u, 0u, 0u, 0u);
+            const float *qq = sq + v * vec;
+#pragma unroll
+            for (int j = 0; j < RW; ++j) {
+                float x[8];
+                if (p.dtype == ARCHI_BF16) {
+                    x[0] = __uint_as_float(d[j].x << 16); x[1] = __uint_as_float(d[j].x & 0xffff0000u);
+                    x[2] = __uint_as_float(d[j].y << 16); x[3] = __uint_as_float(d[j].y & 0xffff0000u);
+                    x[4] = __uint_as_float(d[j].z << 16); x[5] = __uint_as_float(d[j].z & 0xffff0000u);
+                    x[6] = __uint_as_float(d[j].w << 16); x[7] = __uint_as_float(d[j].w & 0xffff0000u);
+                } else {
+                    x[0] = __uint_as_float(d[j].x); x[1] = __uint_as_float(d[j].y);
+                    x[2] = __uint_as_float(d[j].z); x[3] = __uint_as_float(d[j].w);
+                    x[4] = x[5] = x[6] = x[7] = 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (e < vec) {
+                        if (p.metric == ARCHI_L2) {
+                            const float t = x[e] - qq[e];
+                            acc[j] = fmaf(t, t, acc[j]);
+                        } else {
+                            acc[j] = fmaf(x[e], qq[e], acc[j]);
+                        }
                     }
                 }
             }
         }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
-        float sem;                                           // the scan kernel's hybrid key, term by term
-        if (p.metric == ARCHI_L2) {
-            sem = 1.0f - sqrtf(acc);
-        } else if (p.metric == ARCHI_COSINE) {
-            const float n2 = p.norm2[doc];
-            sem = fminf(1.0f, fmaxf(-1.0f, acc * qrn * (n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f)));
-        } else {
-            sem = 1.0f + acc;
+        for (int j = 0; j < RW; ++j) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) acc[j] += __shfl_xor_sync(kFull, acc[j], d);
         }
-        const float key = fmaf(sem, p.w_sem, p.sign * bms[i] * p.w_bm25);
-        list.insert(key, doc, p.k, lane);
+#pragma unroll
+        for (int j = 0; j < RW; ++j) {
+            if (!ok[j]) continue;                                // warp-uniform
+            float sem;                                           // the scan kernel's hybrid key, term by term
+            if (p.metric == ARCHI_L2) {
+                sem = 1.0f - sqrtf(acc[j]);
+            } else if (p.metric == ARCHI_COSINE) {
+                const float n2 = p.norm2[doc[j]];
+                sem = fminf(1.0f, fmaxf(-1.0f, acc[j] * qrn * (n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f)));
+            } else {
+                sem = 1.0f + acc[j];
+            }
+            const float key = fmaf(sem, p.w_sem, p.sign * bms[i0 + j] * p.w_bm25);
+            list.insert(key, doc[j], p.k, lane);
+        }
     }
     // block merge of the 8 warp lists
     constexpr int LEN = 32 * M;
@@ -251,8 +274,8 @@ __global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const 
         WarpTopK<M> res;
         res.init();
         hyb_merge_staged<M>(skey, sid, WARPS, p.k, lane, res);
-        float *ok_ = p.part_key + ((size_t)slot * kHybCps + cta) * p.k;
-        int *oi_ = p.part_id + ((size_t)slot * kHybCps + cta) * p.k;
+        float *ok_ = p.part_key + ((size_t)slot * p.cps + cta) * p.k;
+        int *oi_ = p.part_id + ((size_t)slot * p.cps + cta) * p.k;
 #pragma unroll
         for (int s = 0; s < M; ++s) {
             const int rank = s * 32 + lane;
@@ -267,27 +290,29 @@ __global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const 
 // one warp per query: dense list (combined) + kHybCps partial lists -> the k best
 template <int M>
 __global__ void __launch_bounds__(32) hyb_merge_kernel(const float *dense_comb, const int *dense_id, const float *part_key,
-                                                       const int *part_id, int k, long long id_offset, float *out_scores,
-                                                       long long *out_ids)
+                                                       const int *part_id, int cps, int k, long long id_offset,
+                                                       float *out_scores, long long *out_ids)
 {
     const int slot = blockIdx.x, lane = threadIdx.x;
     WarpTopK<M> res;
     res.init();
+    float tk = -CUDART_INF_F;       // the list's k-th entry: candidates that do not beat it are rejected by one ballot
+    int ti = INT_MAX;
     auto feed = [&](const float *keys, const int *ids, int n) {
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + lane;
             const float ek = i < n ? keys[i] : -CUDART_INF_F;
             const int ei = i < n ? ids[i] : INT_MAX;
-            unsigned cand = __ballot_sync(kFull, ei != INT_MAX);
+            unsigned cand = __ballot_sync(kFull, ei != INT_MAX && better(ek, ei, tk, ti));
             while (cand) {
                 const int src = __ffs(cand) - 1;
                 cand &= cand - 1;
-                res.insert(__shfl_sync(kFull, ek, src), __shfl_sync(kFull, ei, src), k, lane);
+                if (res.insert(__shfl_sync(kFull, ek, src), __shfl_sync(kFull, ei, src), k, lane)) res.threshold(k, tk, ti);
             }
         }
     };
     feed(dense_comb + (size_t)slot * k, dense_id + (size_t)slot * k, k);
-    feed(part_key + (size_t)slot * kHybCps * k, part_id + (size_t)slot * kHybCps * k, kHybCps * k);
+    feed(part_key + (size_t)slot * cps * k, part_id + (size_t)slot * cps * k, cps * k);
 #pragma unroll
     for (int s = 0; s < M; ++s) {
         const int rank = s * 32 + lane;
@@ -360,11 +385,20 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
     if ((rc = hyb_ensure(&w.cand_doc, &w.cand_doc_bytes, cand_need * sizeof(int), false, st)) != ARCHI_OK) return rc;
     if ((rc = hyb_ensure(&w.cand_bm, &w.cand_bm_bytes, cand_need * sizeof(float), false, st)) != ARCHI_OK) return rc;
     if ((rc = hyb_ensure(&w.cand_cnt, &w.cand_cnt_bytes, kHybMaxSlots * sizeof(int), false, st)) != ARCHI_OK) return rc;
-    const size_t list_need = (size_t)kHybMaxSlots * (kHybCps + 1) * kMaxListK;
+    // CTAs per query: about two per SM over the whole round, enough rows per warp to amortise the query staging,
+    // and few enough partial lists (cps * k entries) for the one-warp merge
+    long long max_slot = 1;
+    for (int sl = 0; sl < n_slots; ++sl) max_slot = per_slot[sl] > max_slot ? per_slot[sl] : max_slot;
+    int cps = (2 * s->sm_count) / n_slots;
+    if (cps > kHybCpsMax) cps = kHybCpsMax;
+    if ((long long)cps * 8 * 4 * 8 > max_slot) cps = (int)(max_slot / (8 * 4 * 8));      // >= 8 iterations per warp
+    if ((long long)cps * k > 4096) cps = 4096 / k;
+    if (cps < 1) cps = 1;
+    const size_t list_need = (size_t)kHybMaxSlots * ((size_t)kHybCpsMax * 32 + kMaxListK) + (size_t)kHybMaxSlots * 4096;
     if ((rc = hyb_ensure(&w.part_key, &w.part_key_bytes, list_need * sizeof(float), false, st)) != ARCHI_OK) return rc;
     if ((rc = hyb_ensure(&w.part_id, &w.part_id_bytes, list_need * sizeof(int), false, st)) != ARCHI_OK) return rc;
-    float *dense_comb = w.part_key + (size_t)kHybMaxSlots * kHybCps * kMaxListK;
-    int *dense_id = w.part_id + (size_t)kHybMaxSlots * kHybCps * kMaxListK;
+    float *dense_comb = w.part_key + (size_t)kHybMaxSlots * 4096;       // cps * k <= 4096 entries per slot
+    int *dense_id = w.part_id + (size_t)kHybMaxSlots * 4096;
 
     HybBm25 bm;
     bm.doc_ids = t.doc_ids_dev;
@@ -411,23 +445,24 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
     sp.cand_bm = w.cand_bm;
     sp.part_key = w.part_key;
     sp.part_id = w.part_id;
+    sp.cps = cps;
     const int M = k <= 32 ? 1 : 4;
     const size_t q_bytes = (size_t)s->ld * sizeof(float);
     const size_t m_bytes = (size_t)8 * 32 * M * 8;
     const size_t smem = q_bytes > m_bytes ? q_bytes : m_bytes;
     if (M == 1) {
         if (smem > 40 * 1024) ARCHI_CUDA(cudaFuncSetAttribute((const void *)hyb_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hyb_score_kernel<1><<<n_slots * kHybCps, 256, smem, st>>>(sp, r);
+        hyb_score_kernel<1><<<n_slots * cps, 256, smem, st>>>(sp, r);
     } else {
         if (smem > 40 * 1024) ARCHI_CUDA(cudaFuncSetAttribute((const void *)hyb_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hyb_score_kernel<4><<<n_slots * kHybCps, 256, smem, st>>>(sp, r);
+        hyb_score_kernel<4><<<n_slots * cps, 256, smem, st>>>(sp, r);
     }
     ARCHI_CHECK_LAUNCH();
     if (M == 1)
-        hyb_merge_kernel<1><<<n_slots, 32, 0, st>>>(dense_comb, dense_id, w.part_key, w.part_id, k, id_offset, out_scores,
+        hyb_merge_kernel<1><<<n_slots, 32, 0, st>>>(dense_comb, dense_id, w.part_key, w.part_id, cps, k, id_offset, out_scores,
                                                     reinterpret_cast<long long *>(out_ids));
     else
-        hyb_merge_kernel<4><<<n_slots, 32, 0, st>>>(dense_comb, dense_id, w.part_key, w.part_id, k, id_offset, out_scores,
+        hyb_merge_kernel<4><<<n_slots, 32, 0, st>>>(dense_comb, dense_id, w.part_key, w.part_id, cps, k, id_offset, out_scores,
                                                     reinterpret_cast<long long *>(out_ids));
     ARCHI_CHECK_LAUNCH();
     return ARCHI_OK;

@@ -4,8 +4,8 @@
 // manager.py:373, postgres_vectorstore.py:143,245,390), i.e. sentence-transformers'
 // Pooling(mean) + Normalize modules [external]:
 //     pooled = sum_t h[t]*m[t] / max(sum_t m[t], 1e-9);   out = pooled / max(|pooled|_2, 1e-12)
-// One CTA per sequence.  HBM-bound: the [L, H] slab of a sequence is read once with 16-byte loads
-// (tokens whose mask is 0 are not read at all), the pooled row never leaves the SM, and the
+// One CTA per sequence.  HBM-bound: the [L, H] slab of a sequence is read once with 16-byte streaming loads
+// (tokens whose mask is 0 are not read at all: padding behind the last live token is not visited), the pooled row never leaves the SM, and the
 // normalised row is written once in each requested format -- optionally straight into the tail
 // of the corpus matrix together with its |row|^2 and live bit, so add_documents needs no further
 // kernel.
@@ -13,7 +13,9 @@
 
 namespace archi {
 
-constexpr int kPoolThreads = 256;
+// CTA width: 256 threads for a handful of sequences (more loads in flight per sequence), 128 for large batches --
+// at 40-48 registers a 256-thread CTA fits 6 times on an SM, so 1024 sequences would run as 1.15 waves (the last 136
+// CTAs alone on the machine); 128-thread CTAs fit 10 times: one balanced wave.
 
 struct PoolParams {
     const void *hidden;
@@ -37,7 +39,7 @@ __device__ __forceinline__ float mask_at(const void *mask, size_t i)
 }
 
 // HT = float (VEC 4) or __nv_bfloat16 (VEC 8); H % VEC == 0 is required by the launcher.
-template <typename HT, typename MT>
+template <typename HT, typename MT, int kPoolThreads>
 __global__ void __launch_bounds__(kPoolThreads) pool_normalize_kernel(const PoolParams p)
 {
     constexpr int VEC = sizeof(HT) == 4 ? 4 : 8;
@@ -54,63 +56,61 @@ __global__ void __launch_bounds__(kPoolThreads) pool_normalize_kernel(const Pool
                                (size_t)b * p.L * p.H * sizeof(HT);
     const size_t mbase = (size_t)b * p.L;
 
-    // ---- the mask row: weights to shared memory, their sum, and a compact (deterministic, in token
-    //      order) list of the tokens whose weight is not zero -- masked tokens are never read ----
+    // ---- the mask row: weights to shared memory, their sum and the end of the live range (one barrier).
+    //      Tokens whose weight is zero are never read: padding behind the last live token is not even visited,
+    //      holes inside the range are skipped by a (warp-coherent) branch ----
     float *s_w = spart + (size_t)LS * p.H;               // [L]
-    int *s_live = reinterpret_cast<int *>(s_w + p.L);     // [L]
-    __shared__ int s_wcount[kPoolThreads / 32 + 1];
-    __shared__ int s_nlive;
+    __shared__ int s_end[kPoolThreads / 32];
     float msum = 0.f;
-    int base_live = 0;
-    for (int t0 = 0; t0 < p.L; t0 += kPoolThreads) {
-        const int t = t0 + tid;
-        const float w = t < p.L ? mask_at<MT>(p.mask, mbase + t) : 0.f;
-        if (t < p.L) s_w[t] = w;
+    int last = 0;
+    for (int t = tid; t < p.L; t += kPoolThreads) {
+        const float w = mask_at<MT>(p.mask, mbase + t);
+        s_w[t] = w;
         msum += w;
-        const unsigned bal = __ballot_sync(0xffffffffu, w != 0.f);
-        if (lane == 0) s_wcount[warp] = __popc(bal);
-        __syncthreads();
-        int off = base_live;
-        for (int wi = 0; wi < warp; ++wi) off += s_wcount[wi];
-        if (w != 0.f) s_live[off + __popc(bal & ((1u << lane) - 1u))] = t;
-        int tot = 0;
-        for (int wi = 0; wi < kPoolThreads / 32; ++wi) tot += s_wcount[wi];
-        base_live += tot;
-        __syncthreads();
+        if (w != 0.f) last = t + 1;
     }
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, d);
-    if (lane == 0) s_red[warp] = msum;
-    __syncthreads();
-    if (tid == 0) {
-        float m = 0.f;
-        for (int w = 0; w < kPoolThreads / 32; ++w) m += s_red[w];
-        s_scalar[0] = fmaxf(m, 1e-9f);
-        s_nlive = base_live;
+    for (int d = 16; d >= 1; d >>= 1) {
+        msum += __shfl_xor_sync(0xffffffffu, msum, d);
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+    }
+    if (lane == 0) {
+        s_red[warp] = msum;
+        s_end[warp] = last;
     }
     __syncthreads();
-    const int nlive = s_nlive;
+    int n_tok = 0;
+    {
+        float m = 0.f;
+#pragma unroll
+        for (int w = 0; w < kPoolThreads / 32; ++w) {
+            m += s_red[w];
+            n_tok = max(n_tok, s_end[w]);
+        }
+        if (tid == 0) s_scalar[0] = fmaxf(m, 1e-9f);
+    }
 
-    // masked sums: thread (ls, vc) accumulates live tokens ls, ls+LS, ... of 16-byte column group vc,
-    // eight independent 16-byte loads in flight
+    // masked sums: thread (ls, vc) accumulates tokens ls, ls+LS, ... of 16-byte column group vc, eight
+    // independent 16-byte streaming loads in flight
     if (ls < LS) {
         for (int vc = vc0; vc < nvec; vc += VT) {
             float acc[VEC];
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
             const unsigned char *col = hid + (size_t)vc * VEC * sizeof(HT);
-            for (int i0 = ls; i0 < nlive; i0 += 8 * LS) {
+            for (int t0 = ls; t0 < n_tok; t0 += 8 * LS) {
                 uint4 d[8];
                 float m[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int i = i0 + u * LS;
-                    if (i < nlive) {
-                        const int t = s_live[i];
-                        m[u] = s_w[t];
-                        d[u] = *reinterpret_cast<const uint4 *>(col + (size_t)t * p.H * sizeof(HT));
+                    const int t = t0 + u * LS;
+                    m[u] = t < n_tok ? s_w[t] : 0.f;
+                    if (m[u] != 0.f) {
+                        const unsigned char *ptr = col + (size_t)t * p.H * sizeof(HT);
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(d[u].x), "=r"(d[u].y), "=r"(d[u].z), "=r"(d[u].w)
+                                     : "l"(ptr));
                     } else {
-                        m[u] = 0.f;
                         d[u] = make_uint4(0u, 0u, 0u, 0u);
                     }
                 }
@@ -220,9 +220,10 @@ int launch_pool_normalize(const void *hidden, int hidden_dtype, const void *mask
     ARCHI_REQUIRE(H % VEC == 0, "pool_normalize: H=%d must be a multiple of %d", H, VEC);
     if (B == 0) return ARCHI_OK;
     const int nvec = H / VEC;
-    const int VT = nvec < kPoolThreads ? nvec : kPoolThreads;
-    const int LS = kPoolThreads / VT;
-    const size_t smem = ((size_t)LS * H + 2 * (size_t)L) * sizeof(float);   // partial sums + mask weights + live list
+    const int threads = B >= 512 ? 128 : 256;
+    const int VT = nvec < threads ? nvec : threads;
+    const int LS = threads / VT;
+    const size_t smem = ((size_t)LS * H + (size_t)L) * sizeof(float);   // partial sums + mask weights
     ARCHI_REQUIRE(smem <= 200 * 1024, "pool_normalize: H=%d, L=%d need %zu B of shared memory", H, L, smem);
 
     PoolParams p;
@@ -240,16 +241,23 @@ int launch_pool_normalize(const void *hidden, int hidden_dtype, const void *mask
     p.out_f32 = out_f32;
 
     void (*fn)(const PoolParams);
-    if (hidden_dtype == ARCHI_F32)
-        fn = mask_dtype == ARCHI_I64 ? pool_normalize_kernel<float, long long>
-                                     : pool_normalize_kernel<float, int>;
-    else
-        fn = mask_dtype == ARCHI_I64 ? pool_normalize_kernel<__nv_bfloat16, long long>
-                                     : pool_normalize_kernel<__nv_bfloat16, int>;
+    if (threads == 128) {
+        if (hidden_dtype == ARCHI_F32)
+            fn = mask_dtype == ARCHI_I64 ? pool_normalize_kernel<float, long long, 128> : pool_normalize_kernel<float, int, 128>;
+        else
+            fn = mask_dtype == ARCHI_I64 ? pool_normalize_kernel<__nv_bfloat16, long long, 128>
+                                         : pool_normalize_kernel<__nv_bfloat16, int, 128>;
+    } else {
+        if (hidden_dtype == ARCHI_F32)
+            fn = mask_dtype == ARCHI_I64 ? pool_normalize_kernel<float, long long, 256> : pool_normalize_kernel<float, int, 256>;
+        else
+            fn = mask_dtype == ARCHI_I64 ? pool_normalize_kernel<__nv_bfloat16, long long, 256>
+                                         : pool_normalize_kernel<__nv_bfloat16, int, 256>;
+    }
     if (smem > 48 * 1024)
         ARCHI_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
-    fn<<<B, kPoolThreads, smem, st>>>(p);
+    fn<<<B, threads, smem, st>>>(p);
     ARCHI_CHECK_LAUNCH();
     return ARCHI_OK;
 }

@@ -655,9 +655,10 @@ def run_c5(env, rows=1_000_000, dim=384, n_queries=100):
         rec["batch64_queries_per_s"] = nb * 5 / (e0.elapsed_time(e1) * 1e-3)
         # parity: 8 queries against the oracle's hybrid over the same stored rows and the restated BM25
         checked = failed = 0
-        matched = []
+        matched, paths = [], {}
         for i in range(0, n_queries, max(1, n_queries // 8)):
             sc, ids = store.hybrid_search_terms(lex, [terms[i]], q[i:i + 1], 5, 0.4, 0.6)
+            paths[store.last_hybrid_path] = paths.get(store.last_hybrid_path, 0) + 1
             bm = lex.score(terms[i]).cpu().numpy().astype(np.float64)
             matched.append(int((bm != 0).sum()))
             comb, cid = orc.c_hybrid_topk("cosine", host, qh[i], np.where(bm != 0, bm, np.nan), 0.4, 0.6, 5)
@@ -666,7 +667,7 @@ def run_c5(env, rows=1_000_000, dim=384, n_queries=100):
             checked += 1
             failed += 0 if ok else 1
         rec.update(parity_checked=checked, parity_failed=failed, rows_with_bm25_match_mean=float(np.mean(matched)),
-                   path=store.last_hybrid_path)
+                   paths_of_sampled_queries=paths)
         out["hybrid_" + cname] = rec
     store.close()
     del host, tokens
@@ -852,6 +853,12 @@ def main():
     workloads = {}
     sub_steps = max(5, min(args.steps, 20))
     for w in wanted:
+        # every workload starts from an idle GPU, like the headline did: long tensor-core launches run into the
+        # power cap within a step, and what the previous workload left in the power / thermal integrators would
+        # otherwise decide the next one's clocks
+        import torch as _torch
+        _torch.cuda.synchronize()
+        time.sleep(3.0)
         try:
             if w == "c3":
                 r, d_, st_, k_, b_, cid, desc_ = WORKLOADS["c3"]
