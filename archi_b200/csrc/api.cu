@@ -468,15 +468,21 @@ static int hybrid_terms_impl(archi_store *s, const float *queries, int queries_l
             ARCHI_CUDA(cudaMalloc(&w.dense_ids, need_i));
             w.dense_bytes = need_i;
         }
-        for (int q0 = 0; q0 < nq; q0 += 256) {
-            const int nb = nq - q0 < 256 ? nq - q0 : 256;
-            rc = search_core(s, io.q_dev + (size_t)q0 * s->dim, nb, k, filter, include_deleted, ARCHI_PATH_AUTO, 0, 1.f, 0.f,
-                             nullptr, w.dense_scores + (size_t)q0 * k, w.dense_ids + (size_t)q0 * k, id_offset, st, false, nullptr);
-            if (rc != ARCHI_OK) return rc;
+        // The sparse chain of every round goes to the side stream first (posting walks and row gathers: latency
+        // bound, a few CTAs), the dense search then streams the corpus on the caller's stream beside it; the merges
+        // follow the join.
+        if (!w.side) {
+            ARCHI_CUDA(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
+            ARCHI_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
+            ARCHI_CUDA(cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming));
         }
-        // rounds of <= kHybMaxSlotsHost queries and <= kHybMaxPairsHost terms
+        if ((rc = hybrid_ensure_part_lists(s, nq, st)) != ARCHI_OK) return rc;
+        ARCHI_CUDA(cudaEventRecord(w.ev_fork, st));
+        ARCHI_CUDA(cudaStreamWaitEvent(w.side, w.ev_fork, 0));
+        struct Round { int q0, q1, cps; };
+        std::vector<Round> rounds;
         int q0 = 0;
-        while (q0 < nq) {
+        while (q0 < nq) {          // rounds of <= kHybMaxSlotsHost queries and <= kHybMaxPairsHost terms
             int q1 = q0, pairs = 0;
             while (q1 < nq && q1 - q0 < kHybMaxSlotsHost && pairs + (first[q1 + 1] - first[q1]) <= kHybMaxPairsHost) {
                 pairs += first[q1 + 1] - first[q1];
@@ -485,12 +491,34 @@ static int hybrid_terms_impl(archi_store *s, const float *queries, int queries_l
             std::vector<int> pair_slot(pairs > 0 ? pairs : 1);
             for (int q = q0; q < q1; ++q)
                 for (int j = first[q]; j < first[q + 1]; ++j) pair_slot[j - first[q0]] = q - q0;
-            rc = launch_hybrid_sparse_round(s, io.q_dev + (size_t)q0 * s->dim, q1 - q0, k, w.dense_scores + (size_t)q0 * k,
-                                            w.dense_ids + (size_t)q0 * k, w_sem, w_bm25, t.sign, t, first[q0], pairs,
-                                            pair_slot.data(), filter, include_deleted, io.o_scores + (size_t)q0 * k,
-                                            io.o_ids + (size_t)q0 * k, id_offset, st);
-            if (rc != ARCHI_OK) return rc;
+            int cps = 1;
+            rc = launch_hybrid_sparse_round(s, io.q_dev + (size_t)q0 * s->dim, q1 - q0, k, q0, w_sem, w_bm25, t.sign, t, first[q0],
+                                            pairs, pair_slot.data(), filter, include_deleted, w.side, &cps);
+            if (rc != ARCHI_OK) {
+                cudaEventRecord(w.ev_join, w.side);          // never leave the side stream dangling
+                cudaStreamWaitEvent(st, w.ev_join, 0);
+                return rc;
+            }
+            rounds.push_back({q0, q1, cps});
             q0 = q1;
+        }
+        ARCHI_CUDA(cudaEventRecord(w.ev_join, w.side));
+        // dense top-k of the whole batch (<= 256 queries per call: every failed proof is rescued on the device)
+        for (int d0 = 0; d0 < nq; d0 += 256) {
+            const int nb = nq - d0 < 256 ? nq - d0 : 256;
+            rc = search_core(s, io.q_dev + (size_t)d0 * s->dim, nb, k, filter, include_deleted, ARCHI_PATH_AUTO, 0, 1.f, 0.f,
+                             nullptr, w.dense_scores + (size_t)d0 * k, w.dense_ids + (size_t)d0 * k, id_offset, st, false, nullptr);
+            if (rc != ARCHI_OK) {
+                cudaStreamWaitEvent(st, w.ev_join, 0);
+                return rc;
+            }
+        }
+        ARCHI_CUDA(cudaStreamWaitEvent(st, w.ev_join, 0));
+        for (const Round &rd : rounds) {
+            rc = launch_hybrid_merge(s, rd.q1 - rd.q0, k, rd.q0, rd.cps, w.dense_scores + (size_t)rd.q0 * k,
+                                     w.dense_ids + (size_t)rd.q0 * k, w_sem, io.o_scores + (size_t)rd.q0 * k,
+                                     io.o_ids + (size_t)rd.q0 * k, id_offset, st);
+            if (rc != ARCHI_OK) return rc;
         }
         if (out_path) *out_path = 1;
     } else {

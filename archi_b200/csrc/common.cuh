@@ -114,14 +114,14 @@ struct TensorWorkspace {
 struct HybridWorkspace {
     unsigned long long *acc = nullptr;  size_t acc_bytes = 0;   // [slots][capacity] BM25 sums, 32.32 fixed point, all zero between calls
     bool acc_dirty = false;
-    int *cand_doc = nullptr;            size_t cand_doc_bytes = 0;
-    float *cand_bm = nullptr;           size_t cand_bm_bytes = 0;
-    int *cand_cnt = nullptr;            size_t cand_cnt_bytes = 0;
     float *part_key = nullptr;          size_t part_key_bytes = 0;
     int *part_id = nullptr;             size_t part_id_bytes = 0;
     float *bias = nullptr;              size_t bias_bytes = 0;    // dense-vector fallback: [capacity] BM25 per row
     float *dense_scores = nullptr;      // dense top-k of the batch
     int64_t *dense_ids = nullptr;       size_t dense_bytes = 0;
+    // the sparse chain (posting walks + gathers, latency bound) runs on `side` while the dense search streams the corpus
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 // the query terms of a hybrid search: host arrays indexed by (query, term) occurrence + the device posting lists
@@ -225,12 +225,17 @@ int launch_rescue(archi_store *s, const ScanArgs &a, const int *qsel_dev, const 
                   float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st);
 void free_tensor_workspace(TensorWorkspace &w);
 void free_hybrid_workspace(HybridWorkspace &w);
-// One round of the posting-list hybrid search: n_slots <= 16 queries, n_pairs <= 96 (query, term) pairs starting at
-// pair0 of `t`, pair_slot[j] = query slot of pair j; dense_* = the queries' ordinary top-k (device).
-int launch_hybrid_sparse_round(archi_store *s, const float *q_dev, int n_slots, int k, const float *dense_scores,
-                               const int64_t *dense_ids, float w_sem, float w_bm25, float sign, const HybridTerms &t, int pair0,
-                               int n_pairs, const int *pair_slot, const uint32_t *filter, int include_deleted,
-                               float *out_scores, int64_t *out_ids, int64_t id_offset, cudaStream_t st);
+// One round of the sparse chain of the posting-list hybrid search on stream `st`: n_slots <= 16 queries (slot0 = index
+// of the first one in the call), n_pairs <= 96 (query, term) pairs starting at pair0 of `t`, pair_slot[j] = query slot
+// of pair j.  Leaves the round's partial lists (exact combined scores of the rows matching a term) in the workspace.
+int launch_hybrid_sparse_round(archi_store *s, const float *q_dev, int n_slots, int k, int slot0, float w_sem, float w_bm25,
+                               float sign, const HybridTerms &t, int pair0, int n_pairs, const int *pair_slot,
+                               const uint32_t *filter, int include_deleted, cudaStream_t st, int *out_cps);
+int hybrid_ensure_part_lists(archi_store *s, int nq, cudaStream_t st);
+// dense_* = the queries' ordinary top-k (device) + the round's partial lists -> the k best combined scores
+int launch_hybrid_merge(archi_store *s, int n_slots, int k, int slot0, int cps, const float *dense_scores,
+                        const int64_t *dense_ids, float w_sem, float *out_scores, int64_t *out_ids, int64_t id_offset,
+                        cudaStream_t st);
 int launch_merge_lists(const float *scores, const int64_t *ids, size_t scores_list_stride, size_t ids_list_stride,
                        int n_lists, int nq, int k, int larger_is_better, float *out_scores, int64_t *out_ids,
                        cudaStream_t st);

@@ -6,17 +6,20 @@
 //     exact fused top-k  =  top-k of ( dense top-k over ALL rows  U  exact combined score of S_q )
 // where S_q = rows that match at least one query term: a row outside S_q that is not in the dense top-k is
 // preceded by k rows whose combined score is at least their own dense score, ties included (lower id first).
-// Per batch of queries:
-//   1. the dense top-k of every query -- the ordinary search (tensor-core path for >= 2 queries);
-//   2. hyb_scatter_kernel   walks the posting lists of the query terms and accumulates BM25 per (query, row) into
+// Per batch of queries, on two streams (the sparse chain is a few short latency-bound kernels; the dense search
+// streams the corpus beside it):
+//   side stream
+//   1. hyb_scatter_kernel   walks the posting lists of the query terms and accumulates BM25 per (query, row) into
 //                           a persistent, all-zero accumulator (64-bit fixed point: the sum does not depend on the
 //                           order of the atomics);
-//   3. hyb_fix_dense_kernel turns the dense scores into combined scores and drops dense rows that are in S_q;
-//   4. hyb_collect_kernel   walks the postings again: the first visitor of a row takes its BM25 sum (atomicExch
-//                           back to zero: the accumulator is clean again) and appends the row to the query's list;
-//   5. hyb_score_kernel     a warp per four listed rows: coalesced row loads, exact fp32 dot, combined score,
-//                           warp-register top-k, block merge -> partial lists;
-//   6. hyb_merge_kernel     dense list + partial lists -> the k best (combined desc, id asc).
+//   2. hyb_score_kernel     walks the postings again, 32 per warp: the lane that swaps a row's BM25 sum out of the
+//                           accumulator (atomicExch back to zero: the accumulator is clean again, and a row listed
+//                           under several terms has one owner) scores it -- coalesced row loads four rows at a time,
+//                           exact fp32 dot, combined score, warp-register top-k, block merge -> partial lists;
+//   caller's stream
+//   3. the dense top-k of every query -- the ordinary search (tensor-core path for >= 2 queries);
+//   4. (after the join) hyb_merge_kernel: partial lists + dense list (converted to combined scores, copies of rows
+//                           that are listed in S_q dropped by id) -> the k best (combined desc, id asc).
 // Work per query is O(postings of its terms) + one dense search instead of O(rows) extra traffic and a memset.
 // Queries whose terms match a large part of the corpus (stop-word-like terms) keep the dense-vector scan.
 #include <algorithm>
@@ -30,6 +33,7 @@ namespace archi {
 constexpr int kHybMaxPairs = kHybMaxPairsHost;    // (query, term) pairs per round (kernel-parameter space)
 constexpr int kHybMaxSlots = kHybMaxSlotsHost;    // queries per round (accumulator planes)
 constexpr int kHybCpsMax = 296;     // most CTAs scoring the candidates of one query (cps is chosen per round)
+constexpr int kHybPartStride = 4096;    // partial-list entries per query (cps * k never exceeds it)
 constexpr float kFix = 4294967296.0f;           // 2^32: BM25 contributions are accumulated in 32.32 fixed point
 constexpr float kUnfix = 2.3283064365386963e-10f;
 
@@ -44,7 +48,7 @@ struct HybRound {
     long long total;                       // postings of all pairs
     long long prefix[kHybMaxPairs + 1];    // exclusive prefix sums of the pairs' posting counts
     HybPair pairs[kHybMaxPairs];
-    long long cand_off[kHybMaxSlots + 1];  // where each slot's candidate list starts
+    long long slot_p0[kHybMaxSlots + 1];   // postings [slot_p0[s], slot_p0[s + 1]) of the round belong to query slot s
 };
 
 struct HybBm25 {
@@ -79,47 +83,6 @@ __global__ void __launch_bounds__(256) hyb_scatter_kernel(const HybRound r, cons
     }
 }
 
-// dense (score, id) of the ordinary search -> (combined, local id); rows of S_q are dropped (id = INT_MAX)
-__global__ void hyb_fix_dense_kernel(const float *dense_scores, const long long *dense_ids, int k, int metric, float w_sem,
-                                     long long id_offset, const unsigned long long *acc, long long acc_stride,
-                                     float *comb_out, int *id_out)
-{
-    const int slot = blockIdx.x;
-    for (int rnk = threadIdx.x; rnk < k; rnk += blockDim.x) {
-        const long long gid = dense_ids[(size_t)slot * k + rnk];
-        float comb = -CUDART_INF_F;
-        int id = INT_MAX;
-        if (gid >= 0) {
-            const long long local = gid - id_offset;
-            if (acc[(size_t)slot * acc_stride + local] == 0ull) {
-                const float sc = dense_scores[(size_t)slot * k + rnk];
-                const float sem = metric == ARCHI_COSINE ? sc : 1.0f - sc;     // semantic = 1.0 - (emb <op> q), :441
-                comb = sem * w_sem;
-                id = (int)local;
-            }
-        }
-        comb_out[(size_t)slot * k + rnk] = comb;
-        id_out[(size_t)slot * k + rnk] = id;
-    }
-}
-
-__global__ void __launch_bounds__(256) hyb_collect_kernel(const HybRound r, const HybBm25 bm, unsigned long long *acc,
-                                                          long long acc_stride, int *cand_cnt, int *cand_doc, float *cand_bm)
-{
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < r.total; p += (long long)gridDim.x * blockDim.x) {
-        const int j = hyb_pair_of(r.prefix, r.n_pairs, p);
-        const long long off = r.pairs[j].start + (p - r.prefix[j]);
-        const int doc = bm.doc_ids[off];
-        const int slot = r.pairs[j].slot;
-        const unsigned long long sum = atomicExch(acc + (size_t)slot * acc_stride + doc, 0ull);
-        if (sum != 0ull) {          // first visitor of (slot, doc): owns the row, the accumulator is zero again
-            const int i = atomicAdd(cand_cnt + slot, 1);
-            cand_doc[r.cand_off[slot] + i] = doc;
-            cand_bm[r.cand_off[slot] + i] = __ull2float_rn(sum) * kUnfix;
-        }
-    }
-}
-
 struct HybScore {
     const void *corpus;
     int dtype, dim, ld, metric;
@@ -129,10 +92,10 @@ struct HybScore {
     const float *queries;        // [n_slots, dim] of this round
     float w_sem, w_bm25, sign;
     int k;
-    const int *cand_cnt;
-    const int *cand_doc;
-    const float *cand_bm;
-    float *part_key;             // [n_slots][cps][k]
+    const int32_t *doc_ids;      // the posting lists
+    unsigned long long *acc;     // [slots][acc_stride] BM25 sums of the round (32.32 fixed point), zeroed row by row here
+    long long acc_stride;
+    float *part_key;             // [n_slots][kHybPartStride]: cps lists of k entries per slot
     int *part_id;
     int cps;                     // CTAs per query slot
 };
@@ -181,82 +144,102 @@ __global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const 
     }
     __syncthreads();
     const float qrn = s_qrn;
-    const int n = p.cand_cnt[slot];
-    const int *docs = p.cand_doc + r.cand_off[slot];
-    const float *bms = p.cand_bm + r.cand_off[slot];
     const int vec = p.dtype == ARCHI_BF16 ? 8 : 4;
     const int nvec = p.ld / vec;
     const size_t row_bytes = (size_t)p.ld * (p.dtype == ARCHI_BF16 ? 2 : 4);
+    unsigned long long *acc_slot = p.acc + (size_t)slot * p.acc_stride;
     WarpTopK<M> list;
     list.init();
-    // a warp takes four listed rows at a time and keeps the loads of all four in flight (random 16-byte-vector
-    // gathers are latency bound: one row per warp leaves the memory system idle)
+    // A warp takes 32 postings of the slot at a time, one per lane.  The lane that swaps a row's BM25 sum out of the
+    // accumulator (atomicExch back to zero: the plane is clean for the next call, and a row listed under several
+    // terms has exactly one owner) scores the row; the warp then works through the owned rows four at a time with
+    // the loads of all four in flight (random 16-byte-vector gathers are latency bound).
     constexpr int RW = 4;
-    for (int i0 = (cta * WARPS + warp) * RW; i0 < n; i0 += p.cps * WARPS * RW) {
-        int doc[RW];
-        bool ok[RW];
-        const uint4 *rp[RW];
-        float acc[RW];
-#pragma unroll
-        for (int j = 0; j < RW; ++j) {
-            const int i = i0 + j;
-            doc[j] = i < n ? docs[i] : 0;
-            ok[j] = i < n;
-            if (ok[j] && p.alive) ok[j] = (p.alive[doc[j] >> 5] >> (doc[j] & 31)) & 1u;
-            if (ok[j] && p.filter) ok[j] = (p.filter[doc[j] >> 5] >> (doc[j] & 31)) & 1u;
-            rp[j] = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(p.corpus) + (size_t)doc[j] * row_bytes);
-            acc[j] = 0.f;
+    const long long p_end = r.slot_p0[slot + 1];
+    for (long long pb = r.slot_p0[slot] + (long long)(cta * WARPS + warp) * 32; pb < p_end; pb += (long long)p.cps * WARPS * 32) {
+        const long long pp = pb + lane;
+        int my_doc = 0;
+        float my_bm = 0.f, my_n2 = 1.f;
+        bool own = false;
+        if (pp < p_end) {
+            const int j = hyb_pair_of(r.prefix, r.n_pairs, pp);
+            my_doc = p.doc_ids[r.pairs[j].start + (pp - r.prefix[j])];
+            const unsigned long long sum = atomicExch(acc_slot + my_doc, 0ull);
+            own = sum != 0ull;
+            if (own && p.alive) own = (p.alive[my_doc >> 5] >> (my_doc & 31)) & 1u;
+            if (own && p.filter) own = (p.filter[my_doc >> 5] >> (my_doc & 31)) & 1u;
+            if (own) {
+                my_bm = __ull2float_rn(sum) * kUnfix;
+                if (p.metric == ARCHI_COSINE) my_n2 = p.norm2[my_doc];
+            }
         }
-        for (int v = lane; v < nvec; v += 32) {
-            uint4 d[RW];
-#pragma unroll
-            for (int j = 0; j < RW; ++j) d[j] = ok[j] ? __ldg(rp[j] + v) : make_uint4(0u, 0u, 0u, 0u);
-            const float *qq = sq + v * vec;
+        unsigned owners = __ballot_sync(kFull, own);
+        while (owners) {
+            int doc[RW];
+            bool ok[RW];
+            const uint4 *rp[RW];
+            float acc[RW], bm[RW], n2[RW];
 #pragma unroll
             for (int j = 0; j < RW; ++j) {
-                float x[8];
-                if (p.dtype == ARCHI_BF16) {
-                    x[0] = __uint_as_float(d[j].x << 16); x[1] = __uint_as_float(d[j].x & 0xffff0000u);
-                    x[2] = __uint_as_float(d[j].y << 16); x[3] = __uint_as_float(d[j].y & 0xffff0000u);
-                    x[4] = __uint_as_float(d[j].z << 16); x[5] = __uint_as_float(d[j].z & 0xffff0000u);
-                    x[6] = __uint_as_float(d[j].w << 16); x[7] = __uint_as_float(d[j].w & 0xffff0000u);
-                } else {
-                    x[0] = __uint_as_float(d[j].x); x[1] = __uint_as_float(d[j].y);
-                    x[2] = __uint_as_float(d[j].z); x[3] = __uint_as_float(d[j].w);
-                    x[4] = x[5] = x[6] = x[7] = 0.f;
-                }
+                ok[j] = owners != 0u;
+                const int src = ok[j] ? __ffs(owners) - 1 : 0;
+                if (ok[j]) owners &= owners - 1;
+                doc[j] = __shfl_sync(kFull, my_doc, src);
+                bm[j] = __shfl_sync(kFull, my_bm, src);
+                n2[j] = __shfl_sync(kFull, my_n2, src);
+                rp[j] = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(p.corpus) + (size_t)doc[j] * row_bytes);
+                acc[j] = 0.f;
+            }
+            for (int v = lane; v < nvec; v += 32) {
+                uint4 d[RW];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    if (e < vec) {
-                        if (p.metric == ARCHI_L2) {
-                            const float t = x[e] - qq[e];
-                            acc[j] = fmaf(t, t, acc[j]);
-                        } else {
-                            acc[j] = fmaf(x[e], qq[e], acc[j]);
+                for (int j = 0; j < RW; ++j) d[j] = ok[j] ? __ldg(rp[j] + v) : make_uint4(0u, 0u, 0u, 0u);
+                const float *qq = sq + v * vec;
+#pragma unroll
+                for (int j = 0; j < RW; ++j) {
+                    float x[8];
+                    if (p.dtype == ARCHI_BF16) {
+                        x[0] = __uint_as_float(d[j].x << 16); x[1] = __uint_as_float(d[j].x & 0xffff0000u);
+                        x[2] = __uint_as_float(d[j].y << 16); x[3] = __uint_as_float(d[j].y & 0xffff0000u);
+                        x[4] = __uint_as_float(d[j].z << 16); x[5] = __uint_as_float(d[j].z & 0xffff0000u);
+                        x[6] = __uint_as_float(d[j].w << 16); x[7] = __uint_as_float(d[j].w & 0xffff0000u);
+                    } else {
+                        x[0] = __uint_as_float(d[j].x); x[1] = __uint_as_float(d[j].y);
+                        x[2] = __uint_as_float(d[j].z); x[3] = __uint_as_float(d[j].w);
+                        x[4] = x[5] = x[6] = x[7] = 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        if (e < vec) {
+                            if (p.metric == ARCHI_L2) {
+                                const float t = x[e] - qq[e];
+                                acc[j] = fmaf(t, t, acc[j]);
+                            } else {
+                                acc[j] = fmaf(x[e], qq[e], acc[j]);
+                            }
                         }
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < RW; ++j) {
+            for (int j = 0; j < RW; ++j) {
 #pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) acc[j] += __shfl_xor_sync(kFull, acc[j], d);
-        }
-#pragma unroll
-        for (int j = 0; j < RW; ++j) {
-            if (!ok[j]) continue;                                // warp-uniform
-            float sem;                                           // the scan kernel's hybrid key, term by term
-            if (p.metric == ARCHI_L2) {
-                sem = 1.0f - sqrtf(acc[j]);
-            } else if (p.metric == ARCHI_COSINE) {
-                const float n2 = p.norm2[doc[j]];
-                sem = fminf(1.0f, fmaxf(-1.0f, acc[j] * qrn * (n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f)));
-            } else {
-                sem = 1.0f + acc[j];
+                for (int d = 16; d >= 1; d >>= 1) acc[j] += __shfl_xor_sync(kFull, acc[j], d);
             }
-            const float key = fmaf(sem, p.w_sem, p.sign * bms[i0 + j] * p.w_bm25);
-            list.insert(key, doc[j], p.k, lane);
+#pragma unroll
+            for (int j = 0; j < RW; ++j) {
+                if (!ok[j]) continue;                                // warp-uniform
+                float sem;                                           // the scan kernel's hybrid key, term by term
+                if (p.metric == ARCHI_L2) {
+                    sem = 1.0f - sqrtf(acc[j]);
+                } else if (p.metric == ARCHI_COSINE) {
+                    sem = fminf(1.0f, fmaxf(-1.0f, acc[j] * qrn * (n2[j] > 0.f ? 1.0f / sqrtf(n2[j]) : 0.f)));
+                } else {
+                    sem = 1.0f + acc[j];
+                }
+                const float key = fmaf(sem, p.w_sem, p.sign * bm[j] * p.w_bm25);
+                list.insert(key, doc[j], p.k, lane);
+            }
         }
     }
     // block merge of the 8 warp lists
@@ -274,8 +257,8 @@ __global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const 
         WarpTopK<M> res;
         res.init();
         hyb_merge_staged<M>(skey, sid, WARPS, p.k, lane, res);
-        float *ok_ = p.part_key + ((size_t)slot * p.cps + cta) * p.k;
-        int *oi_ = p.part_id + ((size_t)slot * p.cps + cta) * p.k;
+        float *ok_ = p.part_key + (size_t)slot * kHybPartStride + (size_t)cta * p.k;
+        int *oi_ = p.part_id + (size_t)slot * kHybPartStride + (size_t)cta * p.k;
 #pragma unroll
         for (int s = 0; s < M; ++s) {
             const int rank = s * 32 + lane;
@@ -287,32 +270,92 @@ __global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const 
     }
 }
 
-// one warp per query: dense list (combined) + kHybCps partial lists -> the k best
+// One warp per query: the partial lists of S_q (rows matching a query term, exact combined scores) and the dense
+// top-k of the ordinary search -> the k best.  The dense list comes from a search that ran CONCURRENTLY with the
+// sparse chain, so it is converted here (combined = w_sem * semantic, :441) and de-duplicated here: a dense row that
+// is also in S_q carries a combined score >= its dense-only score.  If its S_q twin is among the k best of S_q, the
+// dense copy is dropped by id; if it is not, k rows of S_q precede the twin and therefore the copy, which then
+// cannot enter the list (`insert` admits only entries better than the current k-th).
+constexpr int kHybMergeThreads = 256;
+
 template <int M>
-__global__ void __launch_bounds__(32) hyb_merge_kernel(const float *dense_comb, const int *dense_id, const float *part_key,
-                                                       const int *part_id, int cps, int k, long long id_offset,
-                                                       float *out_scores, long long *out_ids)
+__global__ void __launch_bounds__(kHybMergeThreads) hyb_merge_kernel(const float *dense_scores, const long long *dense_ids, int metric,
+                                                                     float w_sem, const float *part_key, const int *part_id, int cps,
+                                                                     int part_stride, int k, long long id_offset, float *out_scores,
+                                                                     long long *out_ids)
 {
-    const int slot = blockIdx.x, lane = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char msm[];
+    const int slot = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int n = cps * k;                                  // <= part_stride
+    float *skey = reinterpret_cast<float *>(msm);           // [n] then [k] dense
+    int *sid = reinterpret_cast<int *>(skey + n + k);
+    // every load of the partial lists and of the dense list is issued at once by the whole CTA (a single warp walking
+    // them 32 at a time pays one L2 round trip per step); warp 0 then merges from shared memory
+    for (int i = tid; i < n; i += kHybMergeThreads) {
+        skey[i] = part_key[(size_t)slot * part_stride + i];
+        sid[i] = part_id[(size_t)slot * part_stride + i];
+    }
+    for (int rnk = tid; rnk < k; rnk += kHybMergeThreads) {
+        const long long gid = dense_ids[(size_t)slot * k + rnk];
+        float dk = -CUDART_INF_F;
+        int di = INT_MAX;
+        if (gid >= 0) {
+            const float sc = dense_scores[(size_t)slot * k + rnk];
+            const float sem = metric == ARCHI_COSINE ? sc : 1.0f - sc;     // semantic = 1.0 - (emb <op> q), :441
+            dk = sem * w_sem;
+            di = (int)(gid - id_offset);
+        }
+        skey[n + rnk] = dk;
+        sid[n + rnk] = di;
+    }
+    __syncthreads();
+    if (tid >= 32) return;
     WarpTopK<M> res;
     res.init();
     float tk = -CUDART_INF_F;       // the list's k-th entry: candidates that do not beat it are rejected by one ballot
     int ti = INT_MAX;
-    auto feed = [&](const float *keys, const int *ids, int n) {
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            const float ek = i < n ? keys[i] : -CUDART_INF_F;
-            const int ei = i < n ? ids[i] : INT_MAX;
-            unsigned cand = __ballot_sync(kFull, ei != INT_MAX && better(ek, ei, tk, ti));
-            while (cand) {
-                const int src = __ffs(cand) - 1;
-                cand &= cand - 1;
-                if (res.insert(__shfl_sync(kFull, ek, src), __shfl_sync(kFull, ei, src), k, lane)) res.threshold(k, tk, ti);
-            }
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const float ek = i < n ? skey[i] : -CUDART_INF_F;
+        const int ei = i < n ? sid[i] : INT_MAX;
+        unsigned cand = __ballot_sync(kFull, ei != INT_MAX && better(ek, ei, tk, ti));
+        while (cand) {
+            const int src = __ffs(cand) - 1;
+            cand &= cand - 1;
+            if (res.insert(__shfl_sync(kFull, ek, src), __shfl_sync(kFull, ei, src), k, lane)) res.threshold(k, tk, ti);
         }
-    };
-    feed(dense_comb + (size_t)slot * k, dense_id + (size_t)slot * k, k);
-    feed(part_key + (size_t)slot * cps * k, part_id + (size_t)slot * cps * k, cps * k);
+    }
+    // the dense list: M entries per lane; copies of listed S_q rows are dropped (against the list as it stands BEFORE
+    // any dense entry goes in)
+    float dk[M];
+    int di[M];
+#pragma unroll
+    for (int s = 0; s < M; ++s) {
+        const int rnk = s * 32 + lane;
+        dk[s] = rnk < k ? skey[n + rnk] : -CUDART_INF_F;
+        di[s] = rnk < k ? sid[n + rnk] : INT_MAX;
+    }
+#pragma unroll
+    for (int s = 0; s < M; ++s) {
+        for (int src = 0; src < 32; ++src) {
+            if (s * 32 + src >= k) break;
+            const int id = __shfl_sync(kFull, di[s], src);
+            bool hit = false;
+#pragma unroll
+            for (int u = 0; u < M; ++u) hit = hit || (res.id[u] == id);
+            const bool dup = id != INT_MAX && __any_sync(kFull, hit);
+            if (dup && lane == src) di[s] = INT_MAX;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < M; ++s) {
+        unsigned cand = __ballot_sync(kFull, di[s] != INT_MAX && better(dk[s], di[s], tk, ti));
+        while (cand) {
+            const int src = __ffs(cand) - 1;
+            cand &= cand - 1;
+            if (res.insert(__shfl_sync(kFull, dk[s], src), __shfl_sync(kFull, di[s], src), k, lane)) res.threshold(k, tk, ti);
+        }
+    }
 #pragma unroll
     for (int s = 0; s < M; ++s) {
         const int rank = s * 32 + lane;
@@ -340,11 +383,10 @@ static int hyb_ensure(T **ptr, size_t *cap, size_t need, bool zero, cudaStream_t
     return ARCHI_OK;
 }
 
-int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, dim] */, int n_slots, int k,
-                               const float *dense_scores, const int64_t *dense_ids, float w_sem, float w_bm25, float sign,
-                               const HybridTerms &t, int pair0, int n_pairs, const int *pair_slot,
-                               const uint32_t *filter, int include_deleted, float *out_scores, int64_t *out_ids,
-                               int64_t id_offset, cudaStream_t st)
+int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, dim] */, int n_slots, int k, int slot0,
+                               float w_sem, float w_bm25, float sign, const HybridTerms &t, int pair0, int n_pairs,
+                               const int *pair_slot, const uint32_t *filter, int include_deleted, cudaStream_t st,
+                               int *out_cps)
 {
     ARCHI_REQUIRE(n_slots >= 1 && n_slots <= kHybMaxSlots && n_pairs <= kHybMaxPairs, "hybrid: round too large");
     ARCHI_REQUIRE(k >= 1 && k <= kMaxListK, "hybrid: k=%d out of range for the sparse path", k);
@@ -368,10 +410,10 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
     r.total = run;
     long long off = 0;
     for (int sl = 0; sl < n_slots; ++sl) {
-        r.cand_off[sl] = off;
+        r.slot_p0[sl] = off;
         off += per_slot[sl];
     }
-    r.cand_off[n_slots] = off;
+    r.slot_p0[n_slots] = off;
 
     int rc;
     // the accumulator planes are all-zero between calls (hyb_collect_kernel restores every entry it read)
@@ -381,24 +423,17 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
         else if ((rc = hyb_ensure(&w.acc, &w.acc_bytes, acc_need, true, st)) != ARCHI_OK) return rc;
         w.acc_dirty = false;
     }
-    const size_t cand_need = (size_t)(off > 0 ? off : 1);
-    if ((rc = hyb_ensure(&w.cand_doc, &w.cand_doc_bytes, cand_need * sizeof(int), false, st)) != ARCHI_OK) return rc;
-    if ((rc = hyb_ensure(&w.cand_bm, &w.cand_bm_bytes, cand_need * sizeof(float), false, st)) != ARCHI_OK) return rc;
-    if ((rc = hyb_ensure(&w.cand_cnt, &w.cand_cnt_bytes, kHybMaxSlots * sizeof(int), false, st)) != ARCHI_OK) return rc;
-    // CTAs per query: about two per SM over the whole round, enough rows per warp to amortise the query staging,
-    // and few enough partial lists (cps * k entries) for the one-warp merge
+    // CTAs per query: up to four per SM over the whole round (the kernel is a chain of dependent latencies: posting
+    // -> accumulator swap -> row gather), at least one block of 32 postings per warp, and few enough partial lists
+    // (cps * k entries) for the merge
     long long max_slot = 1;
     for (int sl = 0; sl < n_slots; ++sl) max_slot = per_slot[sl] > max_slot ? per_slot[sl] : max_slot;
-    int cps = (2 * s->sm_count) / n_slots;
+    int cps = (4 * s->sm_count) / n_slots;
     if (cps > kHybCpsMax) cps = kHybCpsMax;
-    if ((long long)cps * 8 * 4 * 8 > max_slot) cps = (int)(max_slot / (8 * 4 * 8));      // >= 8 iterations per warp
-    if ((long long)cps * k > 4096) cps = 4096 / k;
+    if ((long long)cps * 8 * 32 > max_slot) cps = (int)(max_slot / (8 * 32));
+    if ((long long)cps * k > kHybPartStride) cps = kHybPartStride / k;
     if (cps < 1) cps = 1;
-    const size_t list_need = (size_t)kHybMaxSlots * ((size_t)kHybCpsMax * 32 + kMaxListK) + (size_t)kHybMaxSlots * 4096;
-    if ((rc = hyb_ensure(&w.part_key, &w.part_key_bytes, list_need * sizeof(float), false, st)) != ARCHI_OK) return rc;
-    if ((rc = hyb_ensure(&w.part_id, &w.part_id_bytes, list_need * sizeof(int), false, st)) != ARCHI_OK) return rc;
-    float *dense_comb = w.part_key + (size_t)kHybMaxSlots * 4096;       // cps * k <= 4096 entries per slot
-    int *dense_id = w.part_id + (size_t)kHybMaxSlots * 4096;
+    *out_cps = cps;
 
     HybBm25 bm;
     bm.doc_ids = t.doc_ids_dev;
@@ -408,24 +443,13 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
     bm.k1 = t.k1;
     bm.b = t.b;
     const long long acc_stride = s->capacity;
-    w.acc_dirty = true;          // until hyb_collect_kernel has been enqueued
-    ARCHI_CUDA(cudaMemsetAsync(w.cand_cnt, 0, kHybMaxSlots * sizeof(int), st));
+    w.acc_dirty = true;          // until hyb_score_kernel (which swaps every touched entry back to zero) is enqueued
     if (r.total > 0) {
         long long blocks = (r.total + 255) / 256;
         if (blocks > (long long)s->sm_count * 8) blocks = (long long)s->sm_count * 8;
         hyb_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(r, bm, w.acc, acc_stride);
         ARCHI_CHECK_LAUNCH();
     }
-    hyb_fix_dense_kernel<<<n_slots, 128, 0, st>>>(dense_scores, reinterpret_cast<const long long *>(dense_ids), k, s->metric, w_sem,
-                                                  id_offset, w.acc, acc_stride, dense_comb, dense_id);
-    ARCHI_CHECK_LAUNCH();
-    if (r.total > 0) {
-        long long blocks = (r.total + 255) / 256;
-        if (blocks > (long long)s->sm_count * 8) blocks = (long long)s->sm_count * 8;
-        hyb_collect_kernel<<<(unsigned)blocks, 256, 0, st>>>(r, bm, w.acc, acc_stride, w.cand_cnt, w.cand_doc, w.cand_bm);
-        ARCHI_CHECK_LAUNCH();
-    }
-    w.acc_dirty = false;
     HybScore sp;
     sp.corpus = s->data;
     sp.dtype = s->dtype;
@@ -440,11 +464,11 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
     sp.w_bm25 = w_bm25;
     sp.sign = sign;
     sp.k = k;
-    sp.cand_cnt = w.cand_cnt;
-    sp.cand_doc = w.cand_doc;
-    sp.cand_bm = w.cand_bm;
-    sp.part_key = w.part_key;
-    sp.part_id = w.part_id;
+    sp.doc_ids = t.doc_ids_dev;
+    sp.acc = w.acc;
+    sp.acc_stride = acc_stride;
+    sp.part_key = w.part_key + (size_t)slot0 * kHybPartStride;
+    sp.part_id = w.part_id + (size_t)slot0 * kHybPartStride;
     sp.cps = cps;
     const int M = k <= 32 ? 1 : 4;
     const size_t q_bytes = (size_t)s->ld * sizeof(float);
@@ -458,11 +482,38 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
         hyb_score_kernel<4><<<n_slots * cps, 256, smem, st>>>(sp, r);
     }
     ARCHI_CHECK_LAUNCH();
-    if (M == 1)
-        hyb_merge_kernel<1><<<n_slots, 32, 0, st>>>(dense_comb, dense_id, w.part_key, w.part_id, cps, k, id_offset, out_scores,
+    w.acc_dirty = false;
+    return ARCHI_OK;
+}
+
+// The partial lists of a call hold kHybPartStride entries per query (all rounds of the call are in flight at once on
+// the side stream, the merges run after the join).
+int hybrid_ensure_part_lists(archi_store *s, int nq, cudaStream_t st)
+{
+    HybridWorkspace &w = s->hws;
+    int rc;
+    const size_t need = (size_t)(nq > kHybMaxSlots ? nq : kHybMaxSlots) * kHybPartStride;
+    if ((rc = hyb_ensure(&w.part_key, &w.part_key_bytes, need * sizeof(float), false, st)) != ARCHI_OK) return rc;
+    if ((rc = hyb_ensure(&w.part_id, &w.part_id_bytes, need * sizeof(int), false, st)) != ARCHI_OK) return rc;
+    return ARCHI_OK;
+}
+
+// Merge of one round: dense top-k (scores / global ids of the ordinary search) + the round's partial lists.
+int launch_hybrid_merge(archi_store *s, int n_slots, int k, int slot0, int cps, const float *dense_scores,
+                        const int64_t *dense_ids, float w_sem, float *out_scores, int64_t *out_ids, int64_t id_offset,
+                        cudaStream_t st)
+{
+    HybridWorkspace &w = s->hws;
+    const float *pk = w.part_key + (size_t)slot0 * kHybPartStride;
+    const int *pi = w.part_id + (size_t)slot0 * kHybPartStride;
+    const size_t msm = (size_t)(cps * k + k) * 8;           // <= (4096 + 128) * 8 bytes
+    if (k <= 32)
+        hyb_merge_kernel<1><<<n_slots, kHybMergeThreads, msm, st>>>(dense_scores, reinterpret_cast<const long long *>(dense_ids), s->metric, w_sem,
+                                                    pk, pi, cps, kHybPartStride, k, id_offset, out_scores,
                                                     reinterpret_cast<long long *>(out_ids));
     else
-        hyb_merge_kernel<4><<<n_slots, 32, 0, st>>>(dense_comb, dense_id, w.part_key, w.part_id, cps, k, id_offset, out_scores,
+        hyb_merge_kernel<4><<<n_slots, kHybMergeThreads, msm, st>>>(dense_scores, reinterpret_cast<const long long *>(dense_ids), s->metric, w_sem,
+                                                    pk, pi, cps, kHybPartStride, k, id_offset, out_scores,
                                                     reinterpret_cast<long long *>(out_ids));
     ARCHI_CHECK_LAUNCH();
     return ARCHI_OK;
@@ -470,9 +521,12 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
 
 void free_hybrid_workspace(HybridWorkspace &w)
 {
-    void *ptrs[] = {w.acc, w.cand_doc, w.cand_bm, w.cand_cnt, w.part_key, w.part_id, w.bias, w.dense_scores, w.dense_ids};
+    void *ptrs[] = {w.acc, w.part_key, w.part_id, w.bias, w.dense_scores, w.dense_ids};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (w.side) cudaStreamDestroy(w.side);
+    if (w.ev_fork) cudaEventDestroy(w.ev_fork);
+    if (w.ev_join) cudaEventDestroy(w.ev_join);
     w = HybridWorkspace();
 }
 

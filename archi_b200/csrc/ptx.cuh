@@ -57,6 +57,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------
+// 1-D bulk copy global -> shared (no tensor map): 16-byte aligned addresses, size a multiple of 16; completes `bar`
+// with `bytes`.
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const void *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

@@ -795,6 +795,7 @@ struct SelectParams {
     int qt_count, ngroups, cap;
     int k, kprime;            // kprime: rank the selection threshold is taken at (k itself with the margin scheme)
     int margin;               // 1: rescore everything within kMarginMult * eps of the k-th best coarse key
+    int stage_cap;            // keys the shared-memory stage holds (more candidates: the lists are re-walked in L2)
     float *out_scores;
     long long *out_ids;
     long long id_offset;
@@ -845,15 +846,16 @@ __device__ __forceinline__ const uint2 *sel_locate(const SelCommon &c, const int
 }
 
 // s_cnt[SEL_LISTS_MAX], s_off[SEL_LISTS_MAX + 1], s_hist[256 * warps], s_misc[8], s_stage[SEL_STAGE] are
-// shared-memory scratch; returns T, the number of candidates through total_out.  When total <= SEL_STAGE
-// the mapped keys are left in s_stage in concatenated-list order (see sel_locate).
+// shared-memory scratch (s_stage holds stage_cap keys); returns T, the number of candidates through total_out.  When
+// total <= stage_cap the mapped keys are left in s_stage in concatenated-list order (see sel_locate).
+template <int NT>
 __device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int q, int *s_cnt, int *s_off, int *s_hist,
-                                                       int *s_misc, uint32_t *s_stage, int &total_out)
+                                                       int *s_misc, uint32_t *s_stage, int stage_cap, int &total_out)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qt = q / BM, tq = q % BM;
     const int nlists = 2 * c.ngroups;
-    for (int l = tid; l < nlists; l += SEL_THREADS) s_cnt[l] = c.cand_cnt[sel_list_base(c, l, qt) * BM + tq];
+    for (int l = tid; l < nlists; l += NT) s_cnt[l] = c.cand_cnt[sel_list_base(c, l, qt) * BM + tq];
     __syncthreads();
     if (warp == 0) {
         // exclusive prefix sums: lane L owns lists [10 L, 10 L + 10)
@@ -882,19 +884,19 @@ __device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int 
     const int total = s_off[nlists];
     total_out = total;
     if (total <= c.kprime) return 0u;
-    const bool staged = total <= SEL_STAGE;
+    const bool staged = total <= stage_cap;
     if (staged) {
         // one walk over global memory, every load independent of the others (this kernel is latency bound)
-        for (int i0 = tid; i0 < total; i0 += 4 * SEL_THREADS) {
+        for (int i0 = tid; i0 < total; i0 += 4 * NT) {
             uint32_t v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * SEL_THREADS;
+                const int i = i0 + u * NT;
                 if (i < total) v[u] = __ldcg(&sel_locate(c, s_off, nlists, qt, tq, i)->x);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * SEL_THREADS;
+                const int i = i0 + u * NT;
                 if (i < total) s_stage[i] = fmap(__uint_as_float(v[u]));
             }
         }
@@ -908,9 +910,9 @@ __device__ __forceinline__ uint32_t sel_radix_threshold(const SelCommon &c, int 
     int need = c.kprime;                // rank still to be located inside the current prefix bucket
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-        for (int i = tid; i < 256; i += SEL_THREADS) s_hist[i] = 0;
+        for (int i = tid; i < 256; i += NT) s_hist[i] = 0;
         __syncthreads();
-        for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
+        for (int l = warp; l < nlists; l += NT / 32) {
             const int n = s_cnt[l];
             const uint2 *src = c.cand + (sel_list_base(c, l, qt) * BM + tq) * c.cap;
             for (int i = lane; i < n; i += 32) {
@@ -976,7 +978,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_threshold_kernel(const Thresho
     __shared__ int s_misc[8];
     __shared__ uint32_t s_stage[SEL_STAGE];
     int total;
-    const uint32_t T = sel_radix_threshold(p.c, blockIdx.x, s_cnt, s_off, s_hist, s_misc, s_stage, total);
+    const uint32_t T = sel_radix_threshold<SEL_THREADS>(p.c, blockIdx.x, s_cnt, s_off, s_hist, s_misc, s_stage, SEL_STAGE, total);
     if (threadIdx.x == 0 && total > p.c.kprime) {
         const uint32_t Tm = p.margin ? fmap(funmap(T) - kMarginMult * p.qinfo[blockIdx.x].eps) : T;
         atomicMax(p.thr_g + blockIdx.x, Tm);
@@ -1035,22 +1037,26 @@ __global__ void __launch_bounds__(MAXTHR_THREADS) tc_maxima_threshold_kernel(con
     for (int i = lane; i < total; i += 32) valid += keys[i] > none ? 1 : 0;
     valid = __reduce_add_sync(kFull, valid);
     if (valid < p.kprime) return;                    // fewer live rows than kprime seen: no threshold yet
-    const uint32_t T = warp_radix_kth(keys, total, p.kprime, s_hist[warp], lane);
+    const uint32_t T = p.kprime <= 32 ? warp_kth_small(keys, total, p.kprime, lane)
+                                      : warp_radix_kth(keys, total, p.kprime, s_hist[warp], lane);
     if (lane == 0) atomicMax(p.thr_g + q, p.margin ? fmap(funmap(T) - kMarginMult * p.qinfo[q].eps) : T);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectParams p)
+// NT = 256 threads per query, or 128 for batches of more CTAs than fit on the machine at 256 (64 registers per thread:
+// four 256-thread CTAs per SM, eight 128-thread ones -- 1024 queries are then ONE wave of this latency-bound chain).
+template <int NT>
+__global__ void __launch_bounds__(NT) tc_select_kernel(const SelectParams p)
 {
     __shared__ int s_cnt[SEL_LISTS_MAX];            // per-list sizes and their exclusive prefix sums
     __shared__ int s_off[SEL_LISTS_MAX + 1];
-    __shared__ int s_hist[256 * (SEL_THREADS / 32)];
+    __shared__ int s_hist[256 * (NT / 32)];
     __shared__ int s_misc[8];
-    __shared__ uint32_t s_stage[SEL_STAGE];
     __shared__ int s_nk;
     __shared__ uint32_t s_kid[KEPT_MAX];
     __shared__ float s_ex[KEPT_MAX];                // exact key (coarse-key space)
     __shared__ float s_sc[KEPT_MAX];                // output score
-    extern __shared__ __align__(16) float s_q[];    // [ld] the query, zero padded to the row stride
+    extern __shared__ __align__(16) float s_q[];    // [ld] the query, zero padded to the row stride, then the key stage
+    uint32_t *s_stage = reinterpret_cast<uint32_t *>(s_q + p.ld);      // [stage_cap]
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qt = q / BM, tq = q % BM;
     const int nlists = 2 * p.ngroups;
@@ -1063,25 +1069,25 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     sc.kprime = p.kprime;
     if (tid == 0) s_nk = 0;
     // the query is needed last: fetch it first, its latency hides behind the selection
-    for (int e = tid; e < p.ld; e += SEL_THREADS) s_q[e] = e < p.dim ? p.queries[(size_t)q * p.dim + e] : 0.f;
+    for (int e = tid; e < p.ld; e += NT) s_q[e] = e < p.dim ? p.queries[(size_t)q * p.dim + e] : 0.f;
     const QInfo qi = p.qinfo[q];
     int total;
-    uint32_t T = sel_radix_threshold(sc, q, s_cnt, s_off, s_hist, s_misc, s_stage, total);
+    uint32_t T = sel_radix_threshold<NT>(sc, q, s_cnt, s_off, s_hist, s_misc, s_stage, p.stage_cap, total);
     // margin scheme: T is the k-th best coarse key c_k; everything down to c_k - kMarginMult * eps is rescored
     if (p.margin && total > p.kprime) T = fmap(funmap(T) - kMarginMult * qi.eps);
     __syncthreads();
 
     // gather the survivors (key >= T)
-    if (total <= SEL_STAGE) {
+    if (total <= p.stage_cap) {
         // keys are staged in list order: only the survivors' row ids come from global memory
-        for (int i = tid; i < total; i += SEL_THREADS) {
+        for (int i = tid; i < total; i += NT) {
             if (total <= p.kprime || s_stage[i] >= T) {
                 const int slot = atomicAdd(&s_nk, 1);
                 if (slot < KEPT_MAX) s_kid[slot] = __ldcg(&sel_locate(sc, s_off, nlists, qt, tq, i)->y);
             }
         }
     } else {
-        for (int l = warp; l < nlists; l += SEL_THREADS / 32) {
+        for (int l = warp; l < nlists; l += NT / 32) {
             const int n = s_cnt[l];
             const uint2 *src = p.cand + (sel_list_base(sc, l, qt) * BM + tq) * p.cap;
             for (int i = lane; i < n; i += 32) {
@@ -1102,7 +1108,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     const int vec = p.dtype == ARCHI_BF16 ? 8 : 4;
     const int nvec = p.ld / vec;
     const size_t row_bytes = (size_t)p.ld * (p.dtype == ARCHI_BF16 ? 2 : 4);
-    for (int cb = warp * 4; cb < nk; cb += (SEL_THREADS / 32) * 4) {
+    for (int cb = warp * 4; cb < nk; cb += (NT / 32) * 4) {
         size_t row[4];
         const uint4 *rp[4];
         float n2[4], acc[4];
@@ -1173,7 +1179,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
 
     // rank by exact key (ties: lower id) and write the k best
     float ek = -CUDART_INF_F;                         // exact key at rank k-1
-    for (int i = tid; i < nk; i += SEL_THREADS) {
+    for (int i = tid; i < nk; i += NT) {
         const float mine = s_ex[i];
         const int mid = (int)s_kid[i];
         int rank = 0;
@@ -1185,7 +1191,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
         }
         if (rank == p.k - 1) ek = mine;
     }
-    for (int r = nk + tid; r < p.k; r += SEL_THREADS) {
+    for (int r = nk + tid; r < p.k; r += NT) {
         p.out_scores[(size_t)q * p.k + r] = CUDART_NAN_F;
         p.out_ids[(size_t)q * p.k + r] = -1;
     }
@@ -1217,7 +1223,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_kernel(const SelectPara
     }
     __syncthreads();
     if (s_poison) {
-        for (int r = tid; r < p.k; r += SEL_THREADS) {
+        for (int r = tid; r < p.k; r += NT) {
             p.out_scores[(size_t)q * p.k + r] = CUDART_NAN_F;
             p.out_ids[(size_t)q * p.k + r] = -1;
         }
@@ -1649,9 +1655,19 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
     sp.unv_list = w.unv_list;
     sp.max_sel = max_sel;
     sp.sticky = w.sticky_dev;
-    const size_t q_smem = (size_t)s->ld * sizeof(float);
-    if ((rc = set_dyn_smem_once((const void *)tc_select_kernel, (int)q_smem)) != ARCHI_OK) return rc;
-    tc_select_kernel<<<nq, SEL_THREADS, q_smem, st>>>(sp);
+    // The key stage decides how many select CTAs fit on an SM (the kernel is a chain of dependent L2 / HBM latencies:
+    // residency is its throughput).  A probed single-phase scan leaves a few hundred candidates per query (k times
+    // the probe ratio, widened by the margin): 2048 slots -> 8 CTAs per SM, a batch of 1024 queries is one wave.
+    // Long multi-phase scans keep thousands: 7680 slots.  A query that exceeds the stage takes the L2 re-walk path.
+    sp.stage_cap = (probed && n_phases == 1) ? 2048 : SEL_STAGE;
+    const size_t q_smem = (size_t)s->ld * sizeof(float) + (size_t)sp.stage_cap * sizeof(uint32_t);
+    if (nq > 4 * s->sm_count) {
+        if ((rc = set_dyn_smem_once((const void *)tc_select_kernel<128>, (int)q_smem)) != ARCHI_OK) return rc;
+        tc_select_kernel<128><<<nq, 128, q_smem, st>>>(sp);
+    } else {
+        if ((rc = set_dyn_smem_once((const void *)tc_select_kernel<SEL_THREADS>, (int)q_smem)) != ARCHI_OK) return rc;
+        tc_select_kernel<SEL_THREADS><<<nq, SEL_THREADS, q_smem, st>>>(sp);
+    }
     ARCHI_CHECK_LAUNCH();
     // No host round trip here: the caller enqueues the device-driven rescue of the listed queries
     // (launch_rescue with qsel = w.unv_list, nsel = the counter) and reads the verdict when it next

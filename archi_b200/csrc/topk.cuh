@@ -212,6 +212,31 @@ __device__ __forceinline__ uint32_t block_radix_kth(const uint32_t *keys, int to
     return prefix;
 }
 
+// k-th largest of keys[0, total) for k <= 32, one warp: a sorted register list (rank r in lane r) that only keys above
+// the current k-th entry enter -- about k ln(total / k) insertions, no histogram, no shared-memory atomics (scores
+// cluster in a few histogram bins, which serialises the radix passes).  Requires at least k keys > 0.
+__device__ __forceinline__ uint32_t warp_kth_small(const uint32_t *keys, int total, int k, int lane)
+{
+    uint32_t mine = 0u, thr = 0u;
+    for (int i0 = 0; i0 < total; i0 += 32) {
+        const int i = i0 + lane;
+        const uint32_t key = i < total ? keys[i] : 0u;
+        unsigned cand = __ballot_sync(kFull, key > thr);
+        while (cand) {
+            const int src = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const uint32_t nk = __shfl_sync(kFull, key, src);
+            if (nk <= thr) continue;                                  // the threshold rose since the ballot
+            const int p = __popc(__ballot_sync(kFull, mine >= nk));   // entries that stay in front of it
+            const uint32_t up = __shfl_up_sync(kFull, mine, 1);
+            if (lane == p) mine = nk;
+            else if (lane > p) mine = up;
+            thr = __shfl_sync(kFull, mine, k - 1);
+        }
+    }
+    return thr;
+}
+
 // Warp-level variant of block_radix_kth: one warp, its own 256-bin histogram in shared memory, no
 // block barriers.  keys[] (shared memory) are read lane-strided; every lane of the warp must call it.
 __device__ __forceinline__ uint32_t warp_radix_kth(const uint32_t *keys, int total, int k, int *hist, int lane)

@@ -699,20 +699,41 @@ def run_c5(env, rows=1_000_000, dim=384, n_queries=100):
     e1.record()
     torch.cuda.synchronize()
     ms_step = e0.elapsed_time(e1) / n_batches
+    # the pool kernel alone: a CUDA graph of 20 launches, so that no host time sits between them (a launch is
+    # shorter than the Python call that issues it)
     for _ in range(3):
         pool_normalize(hidden, mask, want_bf16=True)
     torch.cuda.synchronize()
-    e0.record()
-    for _ in range(20):
-        pool_normalize(hidden, mask, want_bf16=True)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_pool = e0.elapsed_time(e1) / 20
+    pool_timing = "cuda graph of 20 launches"
+    try:
+        side, graph = torch.cuda.Stream(), torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(20):
+                    pool_normalize(hidden, mask, want_bf16=True)
+        ms_pool = 1e9
+        for _ in range(5):
+            torch.cuda.synchronize()
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_pool = min(ms_pool, e0.elapsed_time(e1) / 20)
+        del graph
+    except Exception as exc:                                   # capture refused: time the plain loop (host-bound)
+        pool_timing = f"loop of 20 Python calls (graph capture failed: {type(exc).__name__})"
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            pool_normalize(hidden, mask, want_bf16=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_pool = e0.elapsed_time(e1) / 20
     live_tokens = int(mask.sum().item())
     pool_bytes = live_tokens * H * 2 + B * L * 8 + B * H * (4 + 2)   # masked tokens are not read
     out["ingest"] = {"chunks_per_s": B / (ms_step * 1e-3), "ms_per_batch": ms_step, "batch": B, "seq_len": L,
                      "encoder": "BertModel MiniLM-L6 shape, random init, bf16 (PyTorch)",
-                     "pool_normalize_ms": ms_pool, "pool_algorithmic_bytes": pool_bytes,
+                     "pool_normalize_ms": ms_pool, "pool_timing": pool_timing, "pool_algorithmic_bytes": pool_bytes,
                      "pool_achieved_GBps": pool_bytes / (ms_pool * 1e-3) / 1e9,
                      "pool_frac_hbm": pool_bytes / (ms_pool * 1e-3) / 1e9 / hbm_peak,
                      "pool_share_of_step": ms_pool / ms_step}

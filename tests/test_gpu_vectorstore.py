@@ -15,9 +15,13 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 @pytest.mark.parametrize("shape", [(6, 24, 64), (3, 256, 384), (33, 17, 768), (2, 5, 1024), (4, 9, 8)])
 @pytest.mark.parametrize("mask_dtype", ["i64", "i32"])
-def test_pool_normalize_matches_oracle(dtype, shape, mask_dtype):
+@pytest.mark.parametrize("ring", ["0", "1"])
+def test_pool_normalize_matches_oracle(dtype, shape, mask_dtype, ring, monkeypatch):
+    """ring=1 forces the cp.async.bulk ring kernel (persistent CTAs) on these small batches, ring=0 the
+    one-CTA-per-sequence kernel; both must agree with the oracle."""
     import torch
     from archi_b200.store import pool_normalize
+    monkeypatch.setenv("ARCHI_POOL_RING", ring)
     B, L, H = shape
     rng = np.random.default_rng(B * 1000 + L)
     hidden = rng.standard_normal(shape).astype(np.float32)
@@ -43,9 +47,50 @@ def test_pool_normalize_matches_oracle(dtype, shape, mask_dtype):
     assert np.array_equal(got_bits, want_bits)
 
 
-def test_pool_normalize_golden_and_all_zero_mask(golden_dir):
+@pytest.mark.parametrize("dtype,shape", [("bf16", (1024, 256, 384)), ("bf16", (700, 64, 768)), ("f32", (600, 40, 1024)),
+                                         ("f32", (2100, 9, 384))])
+def test_pool_normalize_machine_filling_batches(dtype, shape):
+    """Batches of >= 2 sequences per SM take the ring kernel by default: several sequences per persistent CTA,
+    the ring running ahead into the next sequence; all-masked rows, holes, full and one-token sequences included.
+    The one-CTA-per-sequence kernel must give the same rows up to summation order."""
     import torch
     from archi_b200.store import pool_normalize
+    B, L, H = shape
+    rng = np.random.default_rng(B + L)
+    hidden = rng.standard_normal(shape, dtype=np.float32)
+    lens = rng.integers(1, L + 1, size=B)
+    lens[:4] = [L, 1, L, 2]
+    mask = (np.arange(L)[None, :] < lens[:, None]).astype(np.int64)
+    mask[5, :] = 0
+    mask[6, ::3] = 0
+    mask[B - 1, :] = 0
+    h_t = torch.from_numpy(hidden).cuda()
+    if dtype == "bf16":
+        h_t = h_t.to(torch.bfloat16)
+        hidden = h_t.float().cpu().numpy()
+    m_t = torch.from_numpy(mask).cuda()
+    out_f32, out_bf16 = pool_normalize(h_t, m_t, want_bf16=True)
+    got = out_f32.cpu().numpy()
+    want = orc.pool_normalize(hidden, mask)
+    assert np.allclose(got, want, rtol=1e-5, atol=2e-6)
+    assert np.array_equal(got[5], np.zeros(H, dtype=np.float32)) and np.array_equal(got[B - 1], np.zeros(H, dtype=np.float32))
+    assert np.array_equal(out_bf16.view(torch.int16).cpu().numpy().view(np.uint16), orc.f32_to_bf16_bits(got))
+    os.environ["ARCHI_POOL_RING"] = "0"
+    try:
+        other, _ = pool_normalize(h_t, m_t)
+    finally:
+        del os.environ["ARCHI_POOL_RING"]
+    assert np.allclose(other.cpu().numpy(), got, rtol=1e-5, atol=2e-6)
+    # repeated launches are bit-identical (fixed summation order)
+    again, _ = pool_normalize(h_t, m_t)
+    assert torch.equal(again, out_f32)
+
+
+@pytest.mark.parametrize("ring", ["0", "1"])
+def test_pool_normalize_golden_and_all_zero_mask(golden_dir, ring, monkeypatch):
+    import torch
+    from archi_b200.store import pool_normalize
+    monkeypatch.setenv("ARCHI_POOL_RING", ring)
     p = np.load(os.path.join(golden_dir, "pool_6x24x64.npz"))
     out, _ = pool_normalize(torch.from_numpy(p["hidden"]).cuda(), torch.from_numpy(p["mask"]).cuda())
     got = out.cpu().numpy()
@@ -54,9 +99,11 @@ def test_pool_normalize_golden_and_all_zero_mask(golden_dir):
 
 
 @pytest.mark.parametrize("storage", ["f32", "bf16"])
-def test_pool_normalize_append_equals_pool_then_append(storage):
+@pytest.mark.parametrize("ring", ["0", "1"])
+def test_pool_normalize_append_equals_pool_then_append(storage, ring, monkeypatch):
     import torch
     from archi_b200.store import NativeStore, pool_normalize
+    monkeypatch.setenv("ARCHI_POOL_RING", ring)
     rng = np.random.default_rng(4)
     hidden = torch.from_numpy(rng.standard_normal((10, 12, 96)).astype(np.float32)).cuda()
     mask = torch.ones((10, 12), dtype=torch.int64, device="cuda")
