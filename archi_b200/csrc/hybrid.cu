@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const 
     }
 }
 
-// One warp per query: the partial lists of S_q (rows matching a query term, exact combined scores) and the dense
+// One CTA per query (all loads at once, then one warp merges): the partial lists of S_q (rows matching a query term, exact combined scores) and the dense
 // top-k of the ordinary search -> the k best.  The dense list comes from a search that ran CONCURRENTLY with the
 // sparse chain, so it is converted here (combined = w_sem * semantic, :441) and de-duplicated here: a dense row that
 // is also in S_q carries a combined score >= its dense-only score.  If its S_q twin is among the k best of S_q, the

@@ -13,6 +13,8 @@
 //     and the ring keeps filling with the NEXT sequence while the consumer warps reduce / normalise / write the
 //     current one), eight consumer warps accumulate from shared memory;
 //   * pool_normalize_kernel (small batches, rows too wide for the ring): one CTA per sequence, 16-byte streaming loads.
+#include <unordered_map>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -245,6 +247,8 @@ struct RingShape {
     int B;              // sequences
     int tok;            // token rows per chunk
     int chunk_bytes;    // tok * row bytes
+    int *ctr;           // [2] device counters of the launching stream: sequences claimed beyond the first one of
+                        // every CTA, CTAs finished (the last one zeroes both for the next launch)
 };
 
 template <typename HT, typename MT>
@@ -256,6 +260,7 @@ __global__ void __launch_bounds__(kRingThreads) pool_ring_kernel(const PoolParam
     __shared__ float s_red[kRingConsumers / 32];
     __shared__ float s_scalar[2];
     __shared__ int s_ntok[2];
+    __shared__ int s_seq[2];
     __shared__ float s_msum[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -286,11 +291,26 @@ __global__ void __launch_bounds__(kRingThreads) pool_ring_kernel(const PoolParam
 
     if (warp == kRingConsumers / 32) {
         // ---------------- producer ----------------
+        // Sequences are claimed dynamically (the first one is the CTA's own index): lengths differ, and a CTA that
+        // finishes early takes work the slower ones would otherwise still hold when the machine drains.
         unsigned it = 0;
-        int i = 0;
-        for (int b = blockIdx.x; b < g.B; b += gridDim.x, ++i) {
+        int b = blockIdx.x;
+        for (int i = 0;; ++i) {
             const int buf = i & 1;
             ptx::mbar_wait(wempty(buf), ((i >> 1) & 1) ^ 1);
+            if (b >= g.B) {                                       // nothing left: tell the consumers and leave
+                if (lane == 0) {
+                    s_seq[buf] = -1;
+                    ptx::mbar_arrive(wfull(buf));
+                    if (atomicAdd(g.ctr + 1, 1) == (int)gridDim.x - 1) {     // every CTA is past its last claim
+                        g.ctr[0] = 0;
+                        g.ctr[1] = 0;
+                    }
+                }
+                break;
+            }
+            int b_next = 0;                                       // claimed now, needed after this sequence is issued
+            if (lane == 0) b_next = (int)gridDim.x + atomicAdd(g.ctr, 1);
             float msum = 0.f;
             int last = 0;
             const size_t mbase = (size_t)b * p.L;
@@ -307,6 +327,7 @@ __global__ void __launch_bounds__(kRingThreads) pool_ring_kernel(const PoolParam
             }
             if (lane == 0) {
                 s_ntok[buf] = last;
+                s_seq[buf] = b;
                 s_msum[buf] = fmaxf(msum, 1e-9f);
             }
             __syncwarp();
@@ -326,6 +347,7 @@ __global__ void __launch_bounds__(kRingThreads) pool_ring_kernel(const PoolParam
                                    full(st));
                 }
             }
+            b = __shfl_sync(0xffffffffu, b_next, 0);
         }
         return;
     }
@@ -350,10 +372,11 @@ __global__ void __launch_bounds__(kRingThreads) pool_ring_kernel(const PoolParam
         return f;
     };
     unsigned it = 0;
-    int i = 0;
-    for (int b = blockIdx.x; b < g.B; b += gridDim.x, ++i) {
+    for (int i = 0;; ++i) {
         const int buf = i & 1;
         ptx::mbar_wait(wfull(buf), (i >> 1) & 1);
+        const int b = s_seq[buf];
+        if (b < 0) break;
         const int n_tok = s_ntok[buf];
         const float msum = s_msum[buf];
         const uint32_t w_seq = w_s + (uint32_t)(buf * p.L + ls) * 4u;
@@ -411,6 +434,34 @@ __global__ void __launch_bounds__(kRingThreads) pool_ring_kernel(const PoolParam
         if (tid == 0) ptx::mbar_arrive(wempty(buf));
         pool_finish<kRingConsumers, true>(p, b, tid, LS, spart, s_red, s_scalar, msum);
     }
+}
+
+// Two device counters per (device, launching stream) for the ring kernel's dynamic sequence claims.  Launches on
+// one stream are serial and every launch leaves its pair zeroed, so a pair is never shared by two running kernels.
+static int ring_counters(cudaStream_t st, int **out)
+{
+    constexpr int kSlots = 256, kMaxDev = 64;
+    static std::mutex mu;
+    static int *base[kMaxDev] = {};
+    static std::unordered_map<cudaStream_t, int> slot_of[kMaxDev];
+    int dev = 0;
+    ARCHI_CUDA(cudaGetDevice(&dev));
+    ARCHI_REQUIRE(dev >= 0 && dev < kMaxDev, "pool_normalize: device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!base[dev]) {
+        ARCHI_CUDA(cudaMalloc(&base[dev], kSlots * 2 * sizeof(int)));
+        ARCHI_CUDA(cudaMemset(base[dev], 0, kSlots * 2 * sizeof(int)));
+    }
+    auto itr = slot_of[dev].find(st);
+    int slot;
+    if (itr == slot_of[dev].end()) {
+        slot = (int)(slot_of[dev].size() % kSlots);
+        slot_of[dev].emplace(st, slot);
+    } else {
+        slot = itr->second;
+    }
+    *out = base[dev] + 2 * slot;
+    return ARCHI_OK;
 }
 
 // shape of the ring for (row bytes, L); false when the ring kernel does not apply
@@ -481,14 +532,15 @@ int launch_pool_normalize(const void *hidden, int hidden_dtype, const void *mask
             rfn = mask_dtype == ARCHI_I64 ? pool_ring_kernel<__nv_bfloat16, long long> : pool_ring_kernel<__nv_bfloat16, int>;
         if (ring_smem > 48 * 1024)
             ARCHI_CUDA(cudaFuncSetAttribute((const void *)rfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
-        // resident CTAs only, and every CTA gets the same number of sequences (the last ones one fewer)
+        // resident CTAs only (every slot of the machine); they claim sequences until none is left
         int per_sm = 0, dev = 0, sm_count = 0;
         ARCHI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)rfn, kRingThreads, ring_smem));
         ARCHI_CUDA(cudaGetDevice(&dev));
         ARCHI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         const long long max_grid = (long long)sm_count * (per_sm > 0 ? per_sm : 1);
-        const long long per_cta = (B + max_grid - 1) / max_grid;
-        const int ring_grid = (int)((B + per_cta - 1) / per_cta);
+        const int ring_grid = (int)(B < max_grid ? B : max_grid);
+        int rc = ring_counters(st, &g.ctr);
+        if (rc != ARCHI_OK) return rc;
         rfn<<<ring_grid, kRingThreads, ring_smem, st>>>(p, g);
         ARCHI_CHECK_LAUNCH();
         return ARCHI_OK;

@@ -115,11 +115,16 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(const PrepParams p)
         n2 = s_a[0] + s_a[1] + s_a[2] + s_a[3];
         e2 = s_b[0] + s_b[1] + s_b[2] + s_b[3];
         const float qn = sqrtf(n2);
-        // |delta(q.c)| <= unit * |c| :  bf16 queries: |q - bf16(q)| (corpus is exact);
-        // tf32: both operands truncated to 10 mantissa bits -> 2^-9 (1 + 2^-11) |q|;
-        // plus fp32 accumulation slack dim * 2^-22 |q|.
-        float unit = p.tf32 ? 1.0005f * 0.001953125f * qn : sqrtf(e2) * 1.0001f;
-        unit += p.corpus_rel_err * 1.0005f * qn;   // |q~ . (c - bf16(c))| <= |q| 2^-9 |c|
+        // Error of the coarse dot q~.c~ against the exact q.c, term by term, as `unit * |c|` (q~, c~ = the operands
+        // the tensor cores read; |c| = the norm of the row the exact key is defined on):
+        //   (q~ - q).c~     <= |q - bf16(q)| |c~|, and a row rounded to bf16 is at most (1 + 2^-9) longer than the
+        //                      row it rounds -> sqrt(e2) * 1.002 (covers the fp32 rounding of sqrt and of e2 too);
+        //                      kind::tf32: both operands truncated to 10 mantissa bits -> 2^-9 (1 + 2^-11) |q|;
+        //   q.(c~ - c)      <= |q| 2^-9 |c| when the rows read are a bf16 shadow of fp32 rows (0 for bf16 stores:
+        //                      the stored row IS the row), 1.0005 covers the shadow's fp32 normalisation;
+        //   accumulation    <= dim * 2^-22 |q| |c| (fp32 accumulate, exact products).
+        float unit = p.tf32 ? 1.0005f * 0.001953125f * qn : sqrtf(e2) * 1.002f;
+        unit += p.corpus_rel_err * 1.0005f * qn;
         unit += (float)p.dim * 2.4e-7f * qn;
         const float maxn = sqrtf(*p.max_norm2);
         float eps;
