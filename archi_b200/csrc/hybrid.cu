@@ -32,7 +32,7 @@ namespace archi {
 
 constexpr int kHybMaxPairs = kHybMaxPairsHost;    // (query, term) pairs per round (kernel-parameter space)
 constexpr int kHybMaxSlots = kHybMaxSlotsHost;    // queries per round (accumulator planes)
-constexpr int kHybCpsMax = 296;     // most CTAs scoring the candidates of one query (cps is chosen per round)
+constexpr int kHybCpsMax = 592;     // most CTAs scoring the candidates of one query (cps is chosen per round)
 constexpr int kHybPartStride = 4096;    // partial-list entries per query (cps * k never exceeds it)
 constexpr float kFix = 4294967296.0f;           // 2^32: BM25 contributions are accumulated in 32.32 fixed point
 constexpr float kUnfix = 2.3283064365386963e-10f;
@@ -98,6 +98,8 @@ struct HybScore {
     float *part_key;             // [n_slots][kHybPartStride]: cps lists of k entries per slot
     int *part_id;
     int cps;                     // CTAs per query slot
+    int pb;                      // postings a warp claims per step (8, 16 or 32: fewer when there are warps to spare, so
+                                 // that the rows of a step are gathered in one or two rounds of four)
 };
 
 // Merge `nlists` sorted lists of 32*M entries staged in shared memory into `res` (same walk as scan.cu's block merge).
@@ -156,12 +158,12 @@ __global__ void __launch_bounds__(256) hyb_score_kernel(const HybScore p, const 
     // the loads of all four in flight (random 16-byte-vector gathers are latency bound).
     constexpr int RW = 4;
     const long long p_end = r.slot_p0[slot + 1];
-    for (long long pb = r.slot_p0[slot] + (long long)(cta * WARPS + warp) * 32; pb < p_end; pb += (long long)p.cps * WARPS * 32) {
+    for (long long pb = r.slot_p0[slot] + (long long)(cta * WARPS + warp) * p.pb; pb < p_end; pb += (long long)p.cps * WARPS * p.pb) {
         const long long pp = pb + lane;
         int my_doc = 0;
         float my_bm = 0.f, my_n2 = 1.f;
         bool own = false;
-        if (pp < p_end) {
+        if (lane < p.pb && pp < p_end) {
             const int j = hyb_pair_of(r.prefix, r.n_pairs, pp);
             my_doc = p.doc_ids[r.pairs[j].start + (pp - r.prefix[j])];
             const unsigned long long sum = atomicExch(acc_slot + my_doc, 0ull);
@@ -309,22 +311,41 @@ __global__ void __launch_bounds__(kHybMergeThreads) hyb_merge_kernel(const float
         sid[n + rnk] = di;
     }
     __syncthreads();
+    // eight warps reduce a strided eighth of the partial lists each, warp 0 merges their lists
+    constexpr int MW = kHybMergeThreads / 32, LEN = 32 * M;
+    float *wkey = reinterpret_cast<float *>(sid + n + k);   // [MW][LEN]
+    int *wid = reinterpret_cast<int *>(wkey + MW * LEN);
+    {
+        const int warp = tid >> 5;
+        WarpTopK<M> mine;
+        mine.init();
+        float tk = -CUDART_INF_F;   // the list's k-th entry: candidates that do not beat it are rejected by one ballot
+        int ti = INT_MAX;
+        for (int i0 = warp * 32; i0 < n; i0 += MW * 32) {
+            const int i = i0 + lane;
+            const float ek = i < n ? skey[i] : -CUDART_INF_F;
+            const int ei = i < n ? sid[i] : INT_MAX;
+            unsigned cand = __ballot_sync(kFull, ei != INT_MAX && better(ek, ei, tk, ti));
+            while (cand) {
+                const int src = __ffs(cand) - 1;
+                cand &= cand - 1;
+                if (mine.insert(__shfl_sync(kFull, ek, src), __shfl_sync(kFull, ei, src), k, lane)) mine.threshold(k, tk, ti);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < M; ++s) {
+            wkey[warp * LEN + s * 32 + lane] = mine.key[s];
+            wid[warp * LEN + s * 32 + lane] = mine.id[s];
+        }
+    }
+    __syncthreads();
     if (tid >= 32) return;
     WarpTopK<M> res;
     res.init();
-    float tk = -CUDART_INF_F;       // the list's k-th entry: candidates that do not beat it are rejected by one ballot
+    hyb_merge_staged<M>(wkey, wid, MW, k, lane, res);
+    float tk = -CUDART_INF_F;
     int ti = INT_MAX;
-    for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        const float ek = i < n ? skey[i] : -CUDART_INF_F;
-        const int ei = i < n ? sid[i] : INT_MAX;
-        unsigned cand = __ballot_sync(kFull, ei != INT_MAX && better(ek, ei, tk, ti));
-        while (cand) {
-            const int src = __ffs(cand) - 1;
-            cand &= cand - 1;
-            if (res.insert(__shfl_sync(kFull, ek, src), __shfl_sync(kFull, ei, src), k, lane)) res.threshold(k, tk, ti);
-        }
-    }
+    res.threshold(k, tk, ti);
     // the dense list: M entries per lane; copies of listed S_q rows are dropped (against the list as it stands BEFORE
     // any dense entry goes in)
     float dk[M];
@@ -430,10 +451,13 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
     for (int sl = 0; sl < n_slots; ++sl) max_slot = per_slot[sl] > max_slot ? per_slot[sl] : max_slot;
     int cps = (4 * s->sm_count) / n_slots;
     if (cps > kHybCpsMax) cps = kHybCpsMax;
-    if ((long long)cps * 8 * 32 > max_slot) cps = (int)(max_slot / (8 * 32));
     if ((long long)cps * k > kHybPartStride) cps = kHybPartStride / k;
+    if ((long long)cps * 8 * 8 > max_slot) cps = (int)(max_slot / (8 * 8));
     if (cps < 1) cps = 1;
     *out_cps = cps;
+    // postings per warp step: 32 when every warp has several steps of work anyway, fewer when warps would idle
+    int pb = 32;
+    while (pb > 8 && (long long)cps * 8 * pb > max_slot) pb >>= 1;
 
     HybBm25 bm;
     bm.doc_ids = t.doc_ids_dev;
@@ -470,6 +494,7 @@ int launch_hybrid_sparse_round(archi_store *s, const float *q_dev /* [n_slots, d
     sp.part_key = w.part_key + (size_t)slot0 * kHybPartStride;
     sp.part_id = w.part_id + (size_t)slot0 * kHybPartStride;
     sp.cps = cps;
+    sp.pb = pb;
     const int M = k <= 32 ? 1 : 4;
     const size_t q_bytes = (size_t)s->ld * sizeof(float);
     const size_t m_bytes = (size_t)8 * 32 * M * 8;
@@ -506,7 +531,7 @@ int launch_hybrid_merge(archi_store *s, int n_slots, int k, int slot0, int cps, 
     HybridWorkspace &w = s->hws;
     const float *pk = w.part_key + (size_t)slot0 * kHybPartStride;
     const int *pi = w.part_id + (size_t)slot0 * kHybPartStride;
-    const size_t msm = (size_t)(cps * k + k) * 8;           // <= (4096 + 128) * 8 bytes
+    const size_t msm = (size_t)(cps * k + k) * 8 + (size_t)(kHybMergeThreads / 32) * 32 * (k <= 32 ? 1 : 4) * 8;   // < 48 KB
     if (k <= 32)
         hyb_merge_kernel<1><<<n_slots, kHybMergeThreads, msm, st>>>(dense_scores, reinterpret_cast<const long long *>(dense_ids), s->metric, w_sem,
                                                     pk, pi, cps, kHybPartStride, k, id_offset, out_scores,

@@ -472,7 +472,10 @@ static bool ring_shape(int B, int L, int H, int elt, bool forced, RingShape *g, 
     if (nvec > kRingConsumers) return false;
     const size_t row_bytes = (size_t)H * elt;
     const int LS = kRingConsumers / nvec;
-    int tok = (int)(11264 / row_bytes);                     // ~11 KB chunks: four stages + sums fit four CTAs per SM
+    // ~11 KB chunks: four stages + sums fit four CTAs per SM (ARCHI_POOL_CHUNK_KB: experiments)
+    const char *ck = getenv("ARCHI_POOL_CHUNK_KB");
+    const size_t chunk_target = ck && atoi(ck) > 0 ? (size_t)atoi(ck) * 1024 : 11264;
+    int tok = (int)(chunk_target / row_bytes);
     if (tok < LS) tok = LS;
     if (tok < 1) tok = 1;
     if (tok > L) tok = L;
@@ -480,7 +483,7 @@ static bool ring_shape(int B, int L, int H, int elt, bool forced, RingShape *g, 
     g->tok = tok;
     g->chunk_bytes = (int)(tok * row_bytes);
     *smem = (size_t)kRingStages * g->chunk_bytes + ((size_t)LS * H + 2 * (size_t)L) * sizeof(float);
-    if (*smem > 100 * 1024) return false;
+    if (*smem > 200 * 1024) return false;
     int dev = 0, sm_count = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -537,6 +540,8 @@ int launch_pool_normalize(const void *hidden, int hidden_dtype, const void *mask
         ARCHI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)rfn, kRingThreads, ring_smem));
         ARCHI_CUDA(cudaGetDevice(&dev));
         ARCHI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        const char *cps_env = getenv("ARCHI_POOL_CTAS_PER_SM");        // experiments: fewer, fatter CTAs
+        if (cps_env && atoi(cps_env) > 0 && atoi(cps_env) < per_sm) per_sm = atoi(cps_env);
         const long long max_grid = (long long)sm_count * (per_sm > 0 ? per_sm : 1);
         const int ring_grid = (int)(B < max_grid ? B : max_grid);
         int rc = ring_counters(st, &g.ctr);

@@ -1033,17 +1033,39 @@ __global__ void __launch_bounds__(MAXTHR_THREADS) tc_maxima_threshold_kernel(con
         }
     }
     __syncthreads();
-    const int q = q0 + warp;
-    if (warp >= MAXTHR_Q || q >= p.nq) return;
-    const uint32_t *keys = s_mkeys + warp * stride;
-    const uint32_t none = fmap(-CUDART_INF_F);
-    int valid = 0;
+    if (p.kprime > 32) {
+        // large k: one warp per query, radix select over the whole list
+        const int q = q0 + warp;
+        if (warp >= MAXTHR_Q || q >= p.nq) return;
+        const uint32_t *keys = s_mkeys + warp * stride;
+        const uint32_t none = fmap(-CUDART_INF_F);
+        int valid = 0;
 #pragma unroll 8
-    for (int i = lane; i < total; i += 32) valid += keys[i] > none ? 1 : 0;
-    valid = __reduce_add_sync(kFull, valid);
-    if (valid < p.kprime) return;                    // fewer live rows than kprime seen: no threshold yet
-    const uint32_t T = p.kprime <= 32 ? warp_kth_small(keys, total, p.kprime, lane)
-                                      : warp_radix_kth(keys, total, p.kprime, s_hist[warp], lane);
+        for (int i = lane; i < total; i += 32) valid += keys[i] > none ? 1 : 0;
+        valid = __reduce_add_sync(kFull, valid);
+        if (valid < p.kprime) return;                    // fewer live rows than kprime seen: no threshold yet
+        const uint32_t T = warp_radix_kth(keys, total, p.kprime, s_hist[warp], lane);
+        if (lane == 0) atomicMax(p.thr_g + q, p.margin ? fmap(funmap(T) - kMarginMult * p.qinfo[q].eps) : T);
+        return;
+    }
+    // k <= 32: four warps per query, each keeps the 32 largest of a quarter of the maxima (sorted register list);
+    // the first warp of the group then takes the k-th largest of the four lists -- the k-th largest of the union.
+    // s_hist is reused: [MAXTHR_Q][4][32] keys.  Keys of dead chunks map to fmap(-inf): they never count.
+    uint32_t *s_top = reinterpret_cast<uint32_t *>(&s_hist[0][0]);
+    const int grp = warp >> 2, sub = warp & 3;
+    {
+        const uint32_t *keys = s_mkeys + grp * stride;
+        const int quarter = (((total + 3) >> 2) + 31) & ~31;
+        const int begin = sub * quarter, end = min(total, begin + quarter);
+        const uint32_t mine = begin < end ? warp_top32_small(keys, begin, end, p.kprime, lane) : 0u;
+        s_top[(grp * 4 + sub) * 32 + lane] = mine;
+    }
+    __syncthreads();
+    const int q = q0 + grp;
+    if (sub != 0 || q >= p.nq) return;
+    const uint32_t T = warp_kth_small(s_top + grp * 128, 128, p.kprime, lane);
+    // fewer than kprime live maxima seen (T is then 0 or the key of a dead chunk): no threshold yet
+    if (T <= fmap(-CUDART_INF_F)) return;
     if (lane == 0) atomicMax(p.thr_g + q, p.margin ? fmap(funmap(T) - kMarginMult * p.qinfo[q].eps) : T);
 }
 

@@ -212,29 +212,46 @@ __device__ __forceinline__ uint32_t block_radix_kth(const uint32_t *keys, int to
     return prefix;
 }
 
-// k-th largest of keys[0, total) for k <= 32, one warp: a sorted register list (rank r in lane r) that only keys above
-// the current k-th entry enter -- about k ln(total / k) insertions, no histogram, no shared-memory atomics (scores
-// cluster in a few histogram bins, which serialises the radix passes).  Requires at least k keys > 0.
-__device__ __forceinline__ uint32_t warp_kth_small(const uint32_t *keys, int total, int k, int lane)
+// The 32 largest of keys[begin, end) as a sorted register list (rank r in lane r, 0 = no entry; keys are > 0), one warp:
+// only keys above the current k-th entry enter -- about k ln(n / k) insertions, no histogram, no shared-memory atomics
+// (scores cluster in a few histogram bins, which serialises radix passes).  Four 32-key chunks are tested per trip,
+// so the common trip (no key beats the k-th entry) is four independent loads and four ballots.
+__device__ __forceinline__ uint32_t warp_top32_small(const uint32_t *keys, int begin, int end, int k, int lane)
 {
     uint32_t mine = 0u, thr = 0u;
-    for (int i0 = 0; i0 < total; i0 += 32) {
-        const int i = i0 + lane;
-        const uint32_t key = i < total ? keys[i] : 0u;
-        unsigned cand = __ballot_sync(kFull, key > thr);
-        while (cand) {
-            const int src = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const uint32_t nk = __shfl_sync(kFull, key, src);
-            if (nk <= thr) continue;                                  // the threshold rose since the ballot
-            const int p = __popc(__ballot_sync(kFull, mine >= nk));   // entries that stay in front of it
-            const uint32_t up = __shfl_up_sync(kFull, mine, 1);
-            if (lane == p) mine = nk;
-            else if (lane > p) mine = up;
-            thr = __shfl_sync(kFull, mine, k - 1);
+    for (int i0 = begin; i0 < end; i0 += 128) {
+        uint32_t key[4];
+        unsigned cand[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            key[u] = i < end ? keys[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cand[u] = __ballot_sync(kFull, key[u] > thr);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            while (cand[u]) {
+                const int src = __ffs(cand[u]) - 1;
+                cand[u] &= cand[u] - 1;
+                const uint32_t nk = __shfl_sync(kFull, key[u], src);
+                if (nk <= thr) continue;                                  // the threshold rose since the ballot
+                const int p = __popc(__ballot_sync(kFull, mine >= nk));   // entries that stay in front of it
+                const uint32_t up = __shfl_up_sync(kFull, mine, 1);
+                if (lane == p) mine = nk;
+                else if (lane > p) mine = up;
+                thr = __shfl_sync(kFull, mine, k - 1);
+            }
         }
     }
-    return thr;
+    return mine;
+}
+
+// k-th largest of keys[0, total) for k <= 32 (0 when fewer than k keys are > 0), one warp.
+__device__ __forceinline__ uint32_t warp_kth_small(const uint32_t *keys, int total, int k, int lane)
+{
+    const uint32_t mine = warp_top32_small(keys, 0, total, k, lane);
+    return __shfl_sync(kFull, mine, k - 1);
 }
 
 // Warp-level variant of block_radix_kth: one warp, its own 256-bin histogram in shared memory, no

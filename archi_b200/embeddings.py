@@ -50,11 +50,19 @@ class HashTokenizer:
 
 
 class B200Embeddings:
+    """``batch_size=None`` (default) batches by TOKEN BUDGET: consecutive texts share an encoder forward until
+    ``sequences x padded length`` would exceed ``max_batch_tokens``, and the padded length is rounded up to a multiple
+    of 32 -- a forward costs ~20 ms of host time in PyTorch whatever its size, and every new (batch, length) shape
+    costs allocator and GEMM-heuristic work, so few large forwards of a handful of shapes is what makes ingestion
+    GPU-bound (sentence-transformers' fixed 32 texts per forward is not).  An explicit ``batch_size`` restores
+    fixed-count batches padded to the longest member."""
+
     def __init__(self, model_name: str = "sentence-transformers/all-MiniLM-L6-v2", *, model=None,
                  tokenizer: Optional[Callable] = None, device: int = 0, max_seq_length: int = 256,
-                 batch_size: int = 32, dtype: str = "bf16", seed: int = 0):
+                 batch_size: Optional[int] = None, max_batch_tokens: int = 262144, dtype: str = "bf16", seed: int = 0):
         import torch
         self.model_name, self.device, self.max_seq_length, self.batch_size = model_name, int(device), max_seq_length, batch_size
+        self.max_batch_tokens = int(max_batch_tokens)
         self._torch_dtype = torch.bfloat16 if dtype == "bf16" else torch.float32
         self._dev = torch.device("cuda", self.device)
         if model is None:
@@ -88,14 +96,48 @@ class B200Embeddings:
             return HashTokenizer(vocab_size=vocab)
 
     # ---- encoder forward (PyTorch) -> last_hidden_state, attention_mask on the GPU ----------------------
-    def _forward(self, texts: Sequence[str]):
+    def _forward_ids(self, ids: np.ndarray, mask: np.ndarray):
         import torch
-        ids, mask = self.tokenizer(texts, self.max_seq_length)
-        ids_t = torch.from_numpy(ids).to(self._dev, non_blocking=True)
-        mask_t = torch.from_numpy(mask).to(self._dev, non_blocking=True)
+        ids_t = torch.from_numpy(np.ascontiguousarray(ids)).to(self._dev, non_blocking=True)
+        mask_t = torch.from_numpy(np.ascontiguousarray(mask)).to(self._dev, non_blocking=True)
         with torch.inference_mode():
             hidden = self.model(input_ids=ids_t, attention_mask=mask_t).last_hidden_state
         return hidden, mask_t
+
+    def _forward(self, texts: Sequence[str]):
+        ids, mask = self.tokenizer(texts, self.max_seq_length)
+        return self._forward_ids(ids, mask)
+
+    def _batches(self, texts: Sequence[str]):
+        """Yields (hidden [b, L, H], mask [b, L]) over consecutive slices of ``texts``, in order."""
+        if self.batch_size:
+            for s in range(0, len(texts), self.batch_size):
+                yield self._forward(texts[s: s + self.batch_size])
+            return
+        # token budget: tokenise in slices (bounded host memory), then cut each slice where b x padded length
+        # would pass the budget; lengths are rounded up to a multiple of 32 (few distinct shapes)
+        pad_id = int(getattr(self.tokenizer, "pad_id", 0) or 0)
+        for s0 in range(0, len(texts), 4096):
+            ids, mask = self.tokenizer(texts[s0: s0 + 4096], self.max_seq_length)
+            lens = mask.sum(axis=1)
+            n, at = ids.shape[0], 0
+            while at < n:
+                end, longest = at, 1
+                while end < n:
+                    cand = max(longest, int(lens[end]))
+                    padded = min(-(-cand // 32) * 32, max(self.max_seq_length, cand))
+                    if end > at and (end - at + 1) * padded > self.max_batch_tokens:
+                        break
+                    longest = cand
+                    end += 1
+                L = min(-(-longest // 32) * 32, max(self.max_seq_length, longest))
+                b_ids = np.full((end - at, L), pad_id, dtype=np.int64)
+                b_mask = np.zeros((end - at, L), dtype=np.int64)
+                w = min(L, ids.shape[1])
+                b_ids[:, :w] = ids[at:end, :w]
+                b_mask[:, :w] = mask[at:end, :w]
+                yield self._forward_ids(b_ids, b_mask)
+                at = end
 
     @staticmethod
     def _clean(texts: Sequence[str]) -> List[str]:
@@ -107,8 +149,7 @@ class B200Embeddings:
         import torch
         texts = self._clean(texts)
         outs = []
-        for s in range(0, len(texts), self.batch_size):
-            hidden, mask = self._forward(texts[s: s + self.batch_size])
+        for hidden, mask in self._batches(texts):
             out_f32, _ = _store.pool_normalize(hidden, mask)
             outs.append(out_f32)
         return torch.cat(outs, dim=0) if outs else torch.empty((0, self.hidden_size or 0), device=self._dev)
@@ -118,8 +159,7 @@ class B200Embeddings:
         the rows to ``collection``'s GPU store.  Returns the first row id."""
         texts = self._clean(texts)
         first = None
-        for s in range(0, len(texts), self.batch_size):
-            hidden, mask = self._forward(texts[s: s + self.batch_size])
+        for hidden, mask in self._batches(texts):
             native = collection.ensure_native(hidden.shape[-1])
             r0 = native.pool_normalize_append(hidden, mask)
             first = r0 if first is None else first

@@ -52,7 +52,7 @@ def test_config1_add_texts_and_top5(tmp_path):
     from archi_b200.ingest import IngestionDriver
     fx, chunks, metas = _chunks_and_meta()
     assert len(chunks) == fx["n_chunks"] == 120
-    ef = B200Embeddings(dtype="f32", seed=0)
+    ef = B200Embeddings(dtype="f32", seed=0, batch_size=32)       # sentence-transformers' batching: 32 texts per forward
     name = "config1_docs"
     B200VectorStore.drop_collection(name)
     store = B200VectorStore({}, ef, collection_name=name)
@@ -68,6 +68,14 @@ def test_config1_add_texts_and_top5(tmp_path):
     hidden, mask = ef._forward([c.replace("\n", " ") for c in chunks[:32]])
     want = orc.pool_normalize(hidden.float().cpu().numpy(), mask.cpu().numpy())
     assert np.allclose(stored[:32], want, rtol=1e-5, atol=2e-6)
+
+    # the default token-budget batching (one forward for the 120 chunks, lengths padded to a multiple of 32) gives
+    # the same rows up to the encoder's fp32 rounding across batch shapes
+    ef_budget = B200Embeddings(dtype="f32", seed=0)
+    assert ef_budget.batch_size is None
+    rows_budget = ef_budget.embed_documents_device(chunks).cpu().numpy()
+    assert rows_budget.shape == stored.shape and np.allclose(rows_budget, stored, atol=2e-5)
+    del ef_budget
 
     # top-5 through the store surface against the oracle's exact search over the stored rows
     queries = config1_data.queries(chunks, 20)

@@ -86,7 +86,7 @@ def main():
                                 bm25_index=not args.no_bm25)
         if args.dry_run:
             fake = DryNative(ef.dim)
-            store._coll.ensure_native = lambda dim: fake
+            store._coll.ensure_native = lambda dim, shard=0: fake
         driver = IngestionDriver(store, chunk_size=args.chunk_size, commit_batch_size=1 if args.per_file else 25)
         if not args.dry_run:                       # warm-up: CUDA context, encoder autotuning, lazy buffers
             warm = dict(list(files.items())[:8])
