@@ -998,6 +998,7 @@ struct MaxThrParams {
     uint32_t *thr_g;
     const QInfo *qinfo;
     int margin;
+    int one_warp;             // experiments (ARCHI_TC_THR1=1): one warp per query also for k <= 32
 };
 
 constexpr int MAXTHR_Q = 8;            // queries per CTA of tc_maxima_threshold_kernel: one warp each for the selection
@@ -1033,7 +1034,7 @@ __global__ void __launch_bounds__(MAXTHR_THREADS) tc_maxima_threshold_kernel(con
         }
     }
     __syncthreads();
-    if (p.kprime > 32) {
+    if (p.kprime > 32 || p.one_warp) {
         // large k: one warp per query, radix select over the whole list
         const int q = q0 + warp;
         if (warp >= MAXTHR_Q || q >= p.nq) return;
@@ -1044,7 +1045,8 @@ __global__ void __launch_bounds__(MAXTHR_THREADS) tc_maxima_threshold_kernel(con
         for (int i = lane; i < total; i += 32) valid += keys[i] > none ? 1 : 0;
         valid = __reduce_add_sync(kFull, valid);
         if (valid < p.kprime) return;                    // fewer live rows than kprime seen: no threshold yet
-        const uint32_t T = warp_radix_kth(keys, total, p.kprime, s_hist[warp], lane);
+        const uint32_t T = p.kprime <= 32 ? warp_kth_small(keys, total, p.kprime, lane)
+                                          : warp_radix_kth(keys, total, p.kprime, s_hist[warp], lane);
         if (lane == 0) atomicMax(p.thr_g + q, p.margin ? fmap(funmap(T) - kMarginMult * p.qinfo[q].eps) : T);
         return;
     }
@@ -1597,6 +1599,8 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         mp.thr_g = w.thr_g;
         mp.qinfo = reinterpret_cast<const QInfo *>(w.qinfo);
         mp.margin = margin;
+        static const int thr1 = getenv("ARCHI_TC_THR1") ? atoi(getenv("ARCHI_TC_THR1")) : 0;
+        mp.one_warp = thr1;
         const size_t mt_smem = (size_t)MAXTHR_Q * (round_up(nlists * mp.used_slots, 32) + 4) * 4;
         if ((rc = set_dyn_smem_once((const void *)tc_maxima_threshold_kernel, (int)mt_smem)) != ARCHI_OK) return rc;
         tc_maxima_threshold_kernel<<<(nq + MAXTHR_Q - 1) / MAXTHR_Q, MAXTHR_THREADS, mt_smem, st>>>(mp);
