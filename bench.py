@@ -335,6 +335,24 @@ def run_dense(env, name, total_rows, dim, storage, k, batch, cfg_id, desc, steps
     store = NativeStore(dim, "cosine", storage, device=env.local_rank, capacity_rows=cnt)
     # the host keeps the stored values of this rank's shard for the parity check (bf16 bits for bf16 stores)
     keep_host = parity_n > 0
+    parity_note = None
+    if keep_host:
+        # every rank of the box keeps its shard on the host for the check: bounded by the RAM that is actually free
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 1 << 62
+        need = cnt * dim * (2 if storage == "bf16" else 4)
+        fits = 0.0 if need * max(world, 1) > 0.6 * avail else 1.0
+        if world > 1:                       # one decision for the whole job: the check holds collectives
+            t_fit = torch.tensor([fits], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_fit, op=dist.ReduceOp.MIN)
+            fits = float(t_fit.item())
+        if fits < 0.5:
+            keep_host, parity_n = False, 0
+            parity_note = (f"skipped: the shards' host copies ({need * world / 1e9:.0f} GB over the box's ranks) do not fit "
+                           f"in the free host memory ({avail / 1e9:.0f} GB)")
     host = np.empty((cnt, dim), dtype=np.uint16 if storage == "bf16" else np.float32) if keep_host else None
     at = 0
     for x in gen_rows_device(cnt, dim, 1234 + 1000 * cfg_id + rank, dev, data):
@@ -587,6 +605,8 @@ def run_dense(env, name, total_rows, dim, storage, k, batch, cfg_id, desc, steps
         "parity_checked": checked, "parity_failed": failed,
         "parity_how": "sampled queries of the timed batch vs oracle.c over the stored values of every shard (host), merged on rank 0, tie-aware",
     }
+    if parity_note:
+        rec["parity_how"] = parity_note
     if with_e2e:
         rec["e2e"] = {"value": batch / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": batch * dim * 4,
                       "d2h_bytes_per_step": batch * k * 12, "ms_per_step": ms_e2e}
