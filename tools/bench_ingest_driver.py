@@ -62,6 +62,46 @@ class DryNative:
         pass
 
 
+def run(n_files=400, n_paragraphs=40, chunk_size=1000, per_file=False, bm25=True, dry_run=False, ef=None, device=0):
+    """One timed IngestionDriver.add_files over a synthetic corpus; returns the record."""
+    with tempfile.TemporaryDirectory() as root:
+        files = write_corpus(root, n_files, n_paragraphs, seed=5)
+        if dry_run:
+            ef = DryEmbeddings()
+        elif ef is None:
+            import torch
+            from archi_b200 import B200Embeddings
+            assert torch.cuda.is_available(), "needs a GPU (or --dry-run)"
+            ef = B200Embeddings(device=device)
+        kw = {} if dry_run else {"device": device}
+        B200VectorStore.drop_collection("ingest_bench", **kw)
+        store = B200VectorStore({}, ef, collection_name="ingest_bench", storage_dtype="f32" if dry_run else "bf16",
+                                bm25_index=bm25, **kw)
+        if dry_run:
+            fake = DryNative(ef.dim)
+            store._coll.ensure_native = lambda dim, shard=0: fake
+        driver = IngestionDriver(store, chunk_size=chunk_size, commit_batch_size=1 if per_file else 25)
+        if not dry_run:                       # warm-up: CUDA context, encoder autotuning, lazy buffers
+            import torch
+            warm = dict(list(files.items())[:8])
+            driver.add_files(warm)
+            torch.cuda.synchronize()
+            B200VectorStore.drop_collection("ingest_bench", **kw)
+            store = B200VectorStore({}, ef, collection_name="ingest_bench", storage_dtype="bf16", bm25_index=bm25, **kw)
+            driver = IngestionDriver(store, chunk_size=chunk_size, commit_batch_size=1 if per_file else 25)
+        t0 = time.perf_counter()
+        report = driver.add_files(files)
+        if not dry_run:
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out = {"metric": "ingest_chunks_per_sec", "value": report.chunks / dt, "unit": "chunks/s", "files": n_files,
+               "chunks": report.chunks, "seconds": dt, "embed_calls": report.embed_calls, "commits": report.commits,
+               "failed": len(report.failed), "mode": "per-file" if per_file else "cross-file groups of 25",
+               "bm25_index": bm25, "dry_run": dry_run, "embeddings": type(ef).__name__}
+        B200VectorStore.drop_collection("ingest_bench", **kw)
+        return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--files", type=int, default=400)
@@ -71,42 +111,7 @@ def main():
     ap.add_argument("--no-bm25", action="store_true")
     ap.add_argument("--dry-run", action="store_true")
     args = ap.parse_args()
-
-    with tempfile.TemporaryDirectory() as root:
-        files = write_corpus(root, args.files, args.paragraphs, seed=5)
-        if args.dry_run:
-            ef = DryEmbeddings()
-        else:
-            import torch
-            from archi_b200 import B200Embeddings
-            assert torch.cuda.is_available(), "needs a GPU (or --dry-run)"
-            ef = B200Embeddings()
-        B200VectorStore.drop_collection("ingest_bench")
-        store = B200VectorStore({}, ef, collection_name="ingest_bench", storage_dtype="f32" if args.dry_run else "bf16",
-                                bm25_index=not args.no_bm25)
-        if args.dry_run:
-            fake = DryNative(ef.dim)
-            store._coll.ensure_native = lambda dim, shard=0: fake
-        driver = IngestionDriver(store, chunk_size=args.chunk_size, commit_batch_size=1 if args.per_file else 25)
-        if not args.dry_run:                       # warm-up: CUDA context, encoder autotuning, lazy buffers
-            warm = dict(list(files.items())[:8])
-            driver.add_files(warm)
-            torch.cuda.synchronize()
-            B200VectorStore.drop_collection("ingest_bench")
-            store = B200VectorStore({}, ef, collection_name="ingest_bench", storage_dtype="bf16", bm25_index=not args.no_bm25)
-            driver = IngestionDriver(store, chunk_size=args.chunk_size, commit_batch_size=1 if args.per_file else 25)
-        t0 = time.perf_counter()
-        report = driver.add_files(files)
-        if not args.dry_run:
-            torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        out = {"metric": "ingest_chunks_per_sec", "value": report.chunks / dt, "unit": "chunks/s", "files": args.files,
-               "chunks": report.chunks, "seconds": dt, "embed_calls": report.embed_calls, "commits": report.commits,
-               "failed": len(report.failed), "mode": "per-file" if args.per_file else "cross-file groups of 25",
-               "bm25_index": not args.no_bm25, "dry_run": args.dry_run,
-               "embeddings": type(ef).__name__}
-        print(json.dumps(out))
-        B200VectorStore.drop_collection("ingest_bench")
+    print(json.dumps(run(args.files, args.paragraphs, args.chunk_size, args.per_file, not args.no_bm25, args.dry_run)))
 
 
 if __name__ == "__main__":
