@@ -37,6 +37,9 @@ struct ExchangeParams {
     unsigned int *counter;                     // local: CTAs that finished pushing
     int *status;                               // local: 1 = a wait timed out
     unsigned long long timeout_ns;
+    int fence_all;                             // experiments (ARCHI_EXCH_FENCE_ALL=1): every thread fences after its pushes
+    int host_status;                           // experiments (ARCHI_EXCH_HOST_STATUS=1): read the sticky status from host memory
+    int *dev_status;                           // device copy of the sticky status word
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
@@ -61,7 +64,9 @@ __global__ void __launch_bounds__(kExchThreads) exchange_merge_kernel(const Exch
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_last;
     __shared__ int s_bad;      // a wait gave up in this call or in an earlier one: the gather buffer cannot be trusted
-    if (tid == 0) s_bad = *reinterpret_cast<volatile int *>(p.status);
+    // the sticky status lives in pinned host memory (the host checks it before every launch); the kernel reads its
+    // device copy -- a read of host memory from every CTA of every exchange is a PCIe round trip on the critical path
+    if (tid == 0) s_bad = p.host_status ? *reinterpret_cast<volatile int *>(p.status) : *reinterpret_cast<volatile int *>(p.dev_status);
 
     // ---- 1. push my record into slot [parity][rank] of every peer (myself included) ----
     const size_t vecs = p.rec_bytes / 16;
@@ -72,11 +77,16 @@ __global__ void __launch_bounds__(kExchThreads) exchange_merge_kernel(const Exch
         const size_t v = i - (size_t)peer * vecs;
         reinterpret_cast<uint4 *>(p.peer_base[peer] + slot)[v] = src[v];
     }
-    __threadfence_system();
+    // one system-scope fence per CTA, after the barrier that orders every thread's stores before it (fences are
+    // cumulative); a fence by each of the 32k threads serialises in the memory system
+    if (p.fence_all) __threadfence_system();
     __syncthreads();
 
     // ---- 2. the last CTA to finish signals every peer ----
-    if (tid == 0) s_last = atomicAdd(p.counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    if (tid == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(p.counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
     __syncthreads();
     if (s_last) {
         __threadfence_system();
@@ -92,6 +102,7 @@ __global__ void __launch_bounds__(kExchThreads) exchange_merge_kernel(const Exch
         while ((int)(ld_acquire_sys(flag) - p.epoch) < 0) {
             if (global_timer_ns() - t0 > p.timeout_ns) {
                 *reinterpret_cast<volatile int *>(p.status) = 1;      // host-mapped and sticky: the next call fails on the host
+                *reinterpret_cast<volatile int *>(p.dev_status) = 1;
                 __threadfence_system();
                 s_bad = 1;
                 break;
@@ -269,6 +280,11 @@ int archi_exchange_merge_topk(archi_exchange_t *x, const void *record_dev, int n
     p.out_ids = (long long *)out_ids_dev;
     p.counter = reinterpret_cast<unsigned int *>(x->local + x->flags_off + (size_t)x->world * 4);
     p.status = x->d_status;
+    p.dev_status = reinterpret_cast<int *>(x->local + x->flags_off + (size_t)x->world * 4 + 16);
+    static const int fence_all = getenv("ARCHI_EXCH_FENCE_ALL") ? atoi(getenv("ARCHI_EXCH_FENCE_ALL")) : 0;
+    static const int host_status = getenv("ARCHI_EXCH_HOST_STATUS") ? atoi(getenv("ARCHI_EXCH_HOST_STATUS")) : 0;
+    p.fence_all = fence_all;
+    p.host_status = host_status;
     p.timeout_ns = 5ull * 1000 * 1000 * 1000;
     int grid = (nq + archi::kExchThreads / 32 - 1) / (archi::kExchThreads / 32);
     if (grid < 8) grid = 8;
