@@ -998,7 +998,7 @@ struct MaxThrParams {
     uint32_t *thr_g;
     const QInfo *qinfo;
     int margin;
-    int one_warp;             // experiments (ARCHI_TC_THR1=1): one warp per query also for k <= 32
+    int one_warp;             // 1 (default): one warp per query; 0 (ARCHI_TC_THR4=1): four warps per query for k <= 32
 };
 
 constexpr int MAXTHR_Q = 8;            // queries per CTA of tc_maxima_threshold_kernel: one warp each for the selection
@@ -1035,7 +1035,7 @@ __global__ void __launch_bounds__(MAXTHR_THREADS) tc_maxima_threshold_kernel(con
     }
     __syncthreads();
     if (p.kprime > 32 || p.one_warp) {
-        // large k: one warp per query, radix select over the whole list
+        // one warp per query: a sorted register list for k <= 32, radix select over the whole list for larger k
         const int q = q0 + warp;
         if (warp >= MAXTHR_Q || q >= p.nq) return;
         const uint32_t *keys = s_mkeys + warp * stride;
@@ -1599,8 +1599,10 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         mp.thr_g = w.thr_g;
         mp.qinfo = reinterpret_cast<const QInfo *>(w.qinfo);
         mp.margin = margin;
-        static const int thr1 = getenv("ARCHI_TC_THR1") ? atoi(getenv("ARCHI_TC_THR1")) : 0;
-        mp.one_warp = thr1;
+        // ARCHI_TC_THR4=1: four warps per query for k <= 32 (measured slower: 36 vs 23 us at config 2, +11 us per step
+        // on a 125k-row shard), kept for experiments
+        static const int thr4 = getenv("ARCHI_TC_THR4") ? atoi(getenv("ARCHI_TC_THR4")) : 0;
+        mp.one_warp = thr4 ? 0 : 1;
         const size_t mt_smem = (size_t)MAXTHR_Q * (round_up(nlists * mp.used_slots, 32) + 4) * 4;
         if ((rc = set_dyn_smem_once((const void *)tc_maxima_threshold_kernel, (int)mt_smem)) != ARCHI_OK) return rc;
         tc_maxima_threshold_kernel<<<(nq + MAXTHR_Q - 1) / MAXTHR_Q, MAXTHR_THREADS, mt_smem, st>>>(mp);
