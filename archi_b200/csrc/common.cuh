@@ -81,6 +81,8 @@ struct TensorWorkspace {
     int *cand_cnt = nullptr;     size_t cnt_bytes = 0;
     void *aux = nullptr;         size_t aux_bytes = 0;      // [capacity] (a, b) per row
     float *chunkmax = nullptr;   size_t chunkmax_bytes = 0;  // chunk maxima of the probe launch
+    uint32_t *progress = nullptr; size_t progress_bytes = 0; // per-CTA tile counters of a long scan (launch tag | tiles issued)
+    uint32_t launch_tag = 0;
     float *max_norm2 = nullptr;  // device [2]: max / min |row|^2 over live rows
     float h_max_norm2 = 0.f, h_min_norm2 = 0.f;   // host copies (refreshed with maxnorm_epoch)
     // bf16 shadow of an fp32 store: the coarse pass reads it (half the bytes, full-rate MMA); the

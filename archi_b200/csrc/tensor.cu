@@ -231,6 +231,9 @@ struct CoarseParams {
     int cm_slots;         // maxima kept per (CTA, group, query)
     int debug;            // profiling aid (ARCHI_TC_DEBUG): 1 = skip the MMAs, 2 = skip the epilogue math
     int exit_cap;         // buffers larger than this are compacted before the CTA exits
+    int throttle_win;     // > 0: a CTA issues tile u only when every CTA of its corpus group has issued tile u - win
+    uint32_t launch_tag;  // distinguishes this launch's progress words from stale ones (12 bits)
+    uint32_t *progress;   // [grid] (launch_tag << 20) | tiles issued
     const float2 *aux;    // [n] (a, b) per row -- aux mode only
     const uint32_t *alive;   // raw mode: tombstone bitmask (may be null)
     const uint32_t *filter;  // raw mode: per-search filter bitmask (may be null)
@@ -430,7 +433,31 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
                 }
             }
             const uint32_t tx_bytes = (uint32_t)((TWO ? 2 : 1) * stage_bytes);
-            for (int ct = p.tile_begin + group; ct < p.tile_end; ct += p.ngroups) {
+            // Long scans: the CTAs of a corpus group read the same tiles and rely on L2 for all but the first read.
+            // They run at the same tensor-bound pace, but a drift of a fraction of a percent over thousands of
+            // tiles exceeds what L2 holds per group, and the stragglers then fetch every tile from HBM again (ncu,
+            // 10M x 768: 2.2x the algorithmic bytes).  A soft throttle keeps the group inside a window of a few
+            // tiles: every CTA publishes the number of tiles it has issued, and every fourth tile it waits -- bounded,
+            // it never blocks for good -- until the slowest CTA of its group is within the window.
+            volatile uint32_t *prog = p.throttle_win > 0 ? p.progress + (size_t)group * p.qt_count : nullptr;
+            const uint32_t tag = p.launch_tag << 20;
+            int u_t = 0;
+            for (int ct = p.tile_begin + group; ct < p.tile_end; ct += p.ngroups, ++u_t) {
+                if (prog) {
+                    prog[qt] = tag | (uint32_t)u_t;
+                    if (u_t >= p.throttle_win && (u_t & 3) == 0) {
+                        for (int spins = 0; spins < 400; ++spins) {
+                            uint32_t slowest = 0xfffffu;
+                            for (int j = 0; j < p.qt_count; ++j) {
+                                const uint32_t v = prog[j];
+                                const uint32_t pj = (v >> 20) == p.launch_tag ? (v & 0xfffffu) : 0u;   // not started yet: 0
+                                slowest = pj < slowest ? pj : slowest;
+                            }
+                            if ((uint32_t)u_t <= slowest + (uint32_t)p.throttle_win) break;
+                            __nanosleep(200);
+                        }
+                    }
+                }
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
                     const uint32_t sa = ring + s * stage_bytes;
@@ -451,6 +478,7 @@ __device__ __forceinline__ void coarse_body(const CUtensorMap &tmap_q, const CUt
                     }
                 }
             }
+            if (prog) prog[qt] = tag | 0xfffffu;           // done: never hold the others back
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -1543,6 +1571,26 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         cp.a_stages = a_stages;
     }
     cp.exit_cap = cap;           // final launch: nothing to bound (the select kernel walks global memory)
+    {
+        // soft throttle of long scans (see the producer loop): window sized so that the tiles in flight of all groups
+        // stay within about a third of L2; ARCHI_TC_THROTTLE = 0 off, 1 always on, unset = scans of >= 512 tiles per CTA
+        static const int thr_env = getenv("ARCHI_TC_THROTTLE") ? atoi(getenv("ARCHI_TC_THROTTLE")) : -1;
+        const long long tiles_per_cta = n_ctiles / ngroups;
+        const bool on = thr_env == 1 || (thr_env != 0 && qt_count >= 2 && tiles_per_cta >= 512);
+        cp.throttle_win = 0;
+        cp.progress = nullptr;
+        cp.launch_tag = 0;
+        if (on) {
+            const double tile_bytes = (double)BN * (use_shadow ? ld_sh : s->ld) * (tf32 ? 4 : 2);
+            int win = (int)(40e6 / (tile_bytes * ngroups));
+            win = win < 2 ? 2 : (win > 16 ? 16 : win);
+            const bool fresh = !w.progress || w.progress_bytes < (size_t)grid * 4;
+            if ((rc = ensure_buf(&w.progress, &w.progress_bytes, (size_t)grid * 4)) != ARCHI_OK) return rc;
+            if (fresh) ARCHI_CUDA(cudaMemsetAsync(w.progress, 0, w.progress_bytes, st));
+            cp.throttle_win = win;
+            cp.progress = w.progress;
+        }
+    }
     cp.aux = reinterpret_cast<const float2 *>(w.aux);
     cp.alive = alive;
     cp.filter = filter;
@@ -1586,6 +1634,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         cp.maxima_only = 1;
         cp.chunkmax = w.chunkmax;
         cp.cm_slots = cm_slots;
+        cp.launch_tag = (++w.launch_tag) & 0xfffu;
         kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmap_q, tmap_c, cp);
         ARCHI_CHECK_LAUNCH();
         MaxThrParams mp;
@@ -1646,6 +1695,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
         cp.tile_end = bounds[ph + 1];
         cp.resume = ph > 0;
         cp.exit_cap = ph + 1 < n_phases ? cap - BN : cap;   // resumable launches leave room for a whole tile
+        cp.launch_tag = (++w.launch_tag) & 0xfffu;
         kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmap_q, tmap_c, cp);
         ARCHI_CHECK_LAUNCH();
         if (ph + 1 < n_phases) {
@@ -1715,7 +1765,7 @@ int launch_tensor_search(archi_store *s, const float *q_dev, int nq, int k, cons
 void free_tensor_workspace(TensorWorkspace &w)
 {
     void *ptrs[] = {w.qstage, w.qinfo, w.thr_g, w.unverified, w.cand, w.cand_cnt, w.aux, w.max_norm2, w.shadow, w.chunkmax,
-                    w.unv_list, w.sticky_dev};
+                    w.unv_list, w.sticky_dev, w.progress};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (w.h_verdict) cudaFreeHost(w.h_verdict);
