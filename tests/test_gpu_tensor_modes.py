@@ -136,6 +136,13 @@ FORCED = {
                [((40_009, 384, "f32", 10, "cosine", True, 1024), 2)]),
     "split": ({"ARCHI_TC_SPLIT": "1"},
               [((40_009, 1024, "bf16", 10, "cosine", True, 1024), 2)]),
+    # soft throttle of long scans forced on for short ones: every producer publishes its tile count and waits
+    # (bounded) for the slowest CTA of its corpus group -- pair mode, 1-CTA mode, tightening phase, tombstone-free
+    "throttle": ({"ARCHI_TC_THROTTLE": "1"},
+                 [((60_000, 768, "bf16", 10, "cosine", True, 1024), 2),
+                  ((230_000, 384, "f32", 10, "cosine", True, 1024), 2),
+                  ((60_000, 1024, "bf16", 100, "cosine", True, 300), None),
+                  ((40_009, 384, "f32", 10, "l2", False, 100), None)]),
 }
 
 

@@ -250,3 +250,50 @@ def test_probe_threshold_invariant():
             assert thr <= kth_all
             # rows strictly above the threshold are what the main scan admits: at least ... the top ones
             assert (keys > thr).sum() >= min(kprime - 1, (keys > kth_all).sum())
+
+
+def test_token_budget_batching_of_b200_embeddings():
+    """B200Embeddings._batches (host logic, no GPU): consecutive texts share a forward until sequences x padded length
+    would pass max_batch_tokens; lengths are padded to a multiple of 32 (capped at max_seq_length); order, ids and
+    masks are preserved; an explicit batch_size restores fixed-count batches."""
+    import random
+    from archi_b200 import embeddings as E
+
+    class Stub(E.B200Embeddings):
+        def __init__(self, batch_size=None, budget=1024, max_len=64):      # no model, no device
+            self.batch_size, self.max_batch_tokens, self.max_seq_length = batch_size, budget, max_len
+            self.tokenizer = E.HashTokenizer()
+            self.calls = []
+
+        def _forward_ids(self, ids, mask):
+            self.calls.append((ids.copy(), mask.copy()))
+            return ids, mask
+
+        def _forward(self, texts):
+            return self._forward_ids(*self.tokenizer(texts, self.max_seq_length))
+
+    rng = random.Random(1)
+    texts = [" ".join("w%d" % rng.randrange(1000) for _ in range(rng.randint(1, 100))) for _ in range(203)]
+    texts.sort(key=len)                      # what IngestionDriver hands over
+    st = Stub()
+    list(st._batches(texts))
+    shapes = [c[0].shape for c in st.calls]
+    assert sum(s[0] for s in shapes) == len(texts)
+    assert all(s[1] % 32 == 0 and s[1] <= 64 for s in shapes)
+    assert all(s[0] * s[1] <= 1024 or s[0] == 1 for s in shapes)
+    assert len(shapes) < len(texts) / 8                                     # few, large forwards
+    ids_all, mask_all = st.tokenizer(texts, 64)
+    at = 0
+    for ids, mask in st.calls:
+        b, w = ids.shape[0], min(ids.shape[1], ids_all.shape[1])
+        assert np.array_equal(ids[:, :w], ids_all[at:at + b, :w]) and np.array_equal(mask[:, :w], mask_all[at:at + b, :w])
+        assert (mask[:, w:] == 0).all() and (mask.sum(axis=1) >= 2).all()
+        at += b
+    # a single very long text still gets its own forward, truncated to max_seq_length
+    st1 = Stub(budget=16)
+    list(st1._batches(["a " * 500, "b"]))
+    assert [c[0].shape for c in st1.calls] == [(1, 64), (1, 32)]
+    # explicit batch size: fixed-count batches padded to the longest member
+    st2 = Stub(batch_size=32)
+    list(st2._batches(texts))
+    assert [c[0].shape[0] for c in st2.calls] == [32] * 6 + [11]

@@ -3,7 +3,9 @@
 #  A/B  launch lists (device time of every archi kernel launch) of the config-2 and config-3 bench commands
 #  C/D  ncu --set full captures of the dominant kernel (the CTA-pair coarse scorer) for both configs
 #  E    ncu --set full of the pool+normalise kernel and the posting-list hybrid kernels (config 5)
-# Outputs land in gpurun_out/; the summaries under profiles/r02_* are made from them with tools/ncu_digest.py.
+# Outputs land in gpurun_out/; the summaries under profiles/r02_* are made from them with tools/ncu_digest.py and
+# tools/launch_shares.py.  (Mid-round pass; tools/profile_round2_final.sh is the pass on the end-of-round build,
+# tools/profile_throttle.sh the A/B of the soft throttle.)
 NB="--kernel-name-base demangled"
 Q='--no-cpu-baseline --sub-batches "" --parity 0'
 run() { eval "$@"; }

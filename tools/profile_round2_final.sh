@@ -1,5 +1,6 @@
 #!/bin/bash
-# round 2, final single-GPU pass on the end-of-round build: tests, smoke, default bench, launch lists, ncu captures
+# round 2, final single-GPU pass on the end-of-round build (run under gpurun): tests, smoke, default bench, launch
+# lists, ncu captures; the files it leaves in gpurun_out/ are what profiles/r02_* were made from
 set -o pipefail
 timeout 900 python -m pytest tests -m gpu -q --durations=5 2>&1 | tail -30 > gpurun_out/r02z_pytest.log; echo pytest $?
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02z_smoke.log 2>&1; echo smoke $?
