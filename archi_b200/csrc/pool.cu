@@ -449,6 +449,13 @@ static int ring_counters(cudaStream_t st, int **out)
     ARCHI_REQUIRE(dev >= 0 && dev < kMaxDev, "pool_normalize: device index %d out of range", dev);
     std::lock_guard<std::mutex> lock(mu);
     if (!base[dev]) {
+        // the one allocation of this path: not while a stream capture is under way (the caller then takes the other kernel)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            *out = nullptr;
+            return ARCHI_OK;
+        }
         ARCHI_CUDA(cudaMalloc(&base[dev], kSlots * 2 * sizeof(int)));
         ARCHI_CUDA(cudaMemset(base[dev], 0, kSlots * 2 * sizeof(int)));
     }
@@ -525,9 +532,14 @@ int launch_pool_normalize(const void *hidden, int hidden_dtype, const void *mask
     const char *env = getenv("ARCHI_POOL_RING");
     const int mode = env ? atoi(env) : -1;
     RingShape g;
+    g.ctr = nullptr;
     size_t ring_smem = 0;
     if (mode != 0 && (reinterpret_cast<uintptr_t>(hidden) & 15) == 0 &&
         ring_shape(B, L, H, hidden_dtype == ARCHI_F32 ? 4 : 2, mode == 1, &g, &ring_smem)) {
+        int rc = ring_counters(st, &g.ctr);
+        if (rc != ARCHI_OK) return rc;
+    }
+    if (g.ctr != nullptr) {
         void (*rfn)(const PoolParams, const RingShape);
         if (hidden_dtype == ARCHI_F32)
             rfn = mask_dtype == ARCHI_I64 ? pool_ring_kernel<float, long long> : pool_ring_kernel<float, int>;
@@ -544,8 +556,6 @@ int launch_pool_normalize(const void *hidden, int hidden_dtype, const void *mask
         if (cps_env && atoi(cps_env) > 0 && atoi(cps_env) < per_sm) per_sm = atoi(cps_env);
         const long long max_grid = (long long)sm_count * (per_sm > 0 ? per_sm : 1);
         const int ring_grid = (int)(B < max_grid ? B : max_grid);
-        int rc = ring_counters(st, &g.ctr);
-        if (rc != ARCHI_OK) return rc;
         rfn<<<ring_grid, kRingThreads, ring_smem, st>>>(p, g);
         ARCHI_CHECK_LAUNCH();
         return ARCHI_OK;

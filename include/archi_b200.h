@@ -145,7 +145,9 @@ int archi_hybrid_search(archi_store_t *s, const float *queries, int queries_loc,
  * terms: (query, term) occurrences grouped by query -- term_query[j] ascending in [0, nq) --, each with its posting
  * range [post_start[j], post_end[j]) into doc_ids_dev / tfs_dev and its idf (host arrays); doc_len_dev [rows].
  * BM25(row) = sum_j idf[j] * tf*(k1+1) / (tf + k1*(1 - b + b*doc_len[row]/avgdl)) * sign, rows never touched are
- * SQL NULL (COALESCE -> 0).  *out_path (may be NULL): 1 = posting-list path, 2 = dense-vector path. */
+ * SQL NULL (COALESCE -> 0).  *out_path (may be NULL): 1 = posting-list path, 2 = dense-vector path.
+ * The posting walks and row gathers run on an internal stream forked from and joined back into `stream`, beside the
+ * dense search: for the caller the call is ordered on `stream` like every other entry point. */
 typedef struct {
     int n_terms;
     const int32_t *term_query;
